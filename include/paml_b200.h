@@ -1,0 +1,123 @@
+/* paml_b200.h -- C ABI of libpaml_b200.so: the B200 (sm_100a) implementation of PAML's tree-likelihood
+ * hot path.  Plain C types only (pointers, sizes); no torch / C++ types cross this boundary.
+ *
+ * The reference (abacus-gene/paml 4.10.10) has no plugin or FFI layer: its seam is the function pointer
+ * `double (*com.plfun)(double x[], int np)` (src/codeml.c:125, src/baseml.c:70) bound to `lfun`
+ * (src/treesub.c:7764) or `lfundG` (src/treesub.c:7608), plus the globals those functions read.  The entry
+ * points below are what a C binding for that seam needs; each names the reference state it replaces.
+ * paml_b200/host/plfun_b200.inc is that binding (interposed lfun/lfundG calling these functions);
+ * INTEGRATION.md shows how it is compiled against an unmodified reference tree.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (pb200_last_error() gives the
+ * message; the reference itself has no error returns, its `zerror` prints and exits, src/tools.c:1204).
+ * All floating point is IEEE double, as in the reference.  A context owns one GPU and one CUDA stream;
+ * calls on one context must come from one thread at a time (the reference is single-threaded).
+ */
+#ifndef PAML_B200_H
+#define PAML_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb200_ctx pb200_ctx;
+
+/* Spectral-set kinds: which reference P(t) routine a set feeds.  Layout of ONE set (set_stride doubles):
+ *   PB200_KIND_UVROOT   Root[n], U[n*n], V[n*n] (row-major)   PMatUVRoot, src/tools.c:516-546
+ *   PB200_KIND_CIJK     Root[nr], Cijk[n*n*nr]                PMatCijk,   src/baseml.c:1572-1589
+ *   PB200_KIND_K80      kappa                                 PMatK80,    src/tools.c:578-606
+ *   PB200_KIND_JC69LIKE (nothing)                             PMatJC69like, src/codeml.c:3585-3594       */
+enum { PB200_KIND_UVROOT = 0, PB200_KIND_CIJK = 1, PB200_KIND_K80 = 2, PB200_KIND_JC69LIKE = 3 };
+
+/* Which reference function's arithmetic pb200_eval reproduces:
+ *   PB200_SEM_LFUN    lfun   (src/treesub.c:7764-7807): one class, f_h <= 0 -> 1e-80
+ *   PB200_SEM_LFUNDG  fx_r + lfundG (src/treesub.c:7696-7761, 7608-7660): class mixture with freqK,
+ *                     log-sum-exp form when scaling nodes exist, f_h <= 0 -> 1e-300                      */
+enum { PB200_SEM_LFUN = 0, PB200_SEM_LFUNDG = 1 };
+
+/* Create / destroy a context bound to CUDA device `device`.  Fails loudly (non-zero + message) when no
+ * usable sm_100 GPU is present: there is no CPU fallback. */
+int pb200_create(pb200_ctx **out, int device);
+void pb200_destroy(pb200_ctx *ctx);
+/* Message of the last failing call on this thread ("" if none). */
+const char *pb200_last_error(void);
+/* Library / build description string (arch, version). */
+const char *pb200_version(void);
+
+/* Replaces com.z / com.fpatt / com.cleandata / nChara / CharaMap (src/codeml.c:110, src/treesub.c:1116-1286,
+ * src/tools.c:20): uploads this context's site patterns.
+ *   n        com.ncode (<= 64)           ns     number of tips
+ *   npatt    patterns held by THIS context (a shard when several GPUs split the alignment)
+ *   z        [ns][npatt] coded tip states, 0..n-1 resolved, >= n index nchara/charamap
+ *   fpatt    [npatt] pattern weights     cleandata  com.cleandata
+ *   nchara   [256], charamap [256][64]   ambiguity sets (may be NULL when every z < n)                    */
+int pb200_set_data(pb200_ctx *ctx, int n, int ns, long long npatt, const unsigned char *z,
+                   const double *fpatt, int cleandata, const unsigned char *nchara,
+                   const unsigned char *charamap);
+
+/* Replaces nodes[].nson/sons + tree.root (src/codeml.c:138-147) and com.nodeScale (src/treesub.c:7141-7198):
+ * the topology and the nodes at which conditional vectors are rescaled.  Tips are nodes 0..ns-1.
+ *   sons        [nnode][maxsons], unused entries ignored
+ *   scale_flags [nnode] or NULL (no scaling); the root entry is ignored                                  */
+int pb200_set_tree(pb200_ctx *ctx, int nnode, int root, const int *nson, const int *sons, int maxsons,
+                   const unsigned char *scale_flags);
+
+/* Restatement of SetNodeScale (src/treesub.c:7178-7198) for callers that do not have the reference's flags:
+ * writes flags[nnode], returns the number of scaling nodes.  every = 100 (baseml), 15 (codon), 50 (aa).   */
+int pb200_default_scale_flags(int nnode, int root, const int *nson, const int *sons, int maxsons,
+                              int every, unsigned char *flags);
+
+/* One likelihood evaluation = one call of com.plfun after SetParameters(x) (src/treesub.c:7764 / 7608):
+ * batched P(t) for every (class, branch), Felsenstein pruning of every pattern of this context, root
+ * reduction with pi, class mixture, weighting by fpatt, deterministic sum; if a communicator was set up
+ * (pb200_comm_init) one ncclAllReduce of the scalar.  Host buffers in, one double out.
+ *   nclass, freqK[nclass]     com.ncatG / com.freqK (1 / {1} for PB200_SEM_LFUN)
+ *   set_kind, nr, nset, set_stride, set_data[nset][set_stride]   spectral sets, layout above
+ *   branch_set[nclass][nnode] which set branch (class, node) uses (root entry ignored)
+ *   branch_t  [nclass][nnode] its t, all factors applied (rate class, rgene / branch rate, Qfactor)
+ *   pi[n]                     com.pi
+ *   neg_lnL                   out: minus log-likelihood, the value com.plfun returns                     */
+int pb200_eval(pb200_ctx *ctx, int semantics, int nclass, const double *freqK, int set_kind, int nr,
+               int nset, long long set_stride, const double *set_data, const int *branch_set,
+               const double *branch_t, const double *pi, double *neg_lnL);
+
+/* Per-pattern outputs of the last pb200_eval on this context (this context's shard only):
+ *   lnf[npatt]          log f_h, what the reference stores in dfsites[] / prints to `lnf`
+ *                       (src/treesub.c:7801-7803, 7655-7656)
+ *   fhK[nclass][npatt]  com.fhK as left by fx_r (src/treesub.c:7743-7750)                                */
+int pb200_get_lnf(pb200_ctx *ctx, double *lnf);
+int pb200_get_fhK(pb200_ctx *ctx, double *fhK);
+
+/* The batched P(t) kernel on its own (what GetPMatBranch computes, src/treesub.c:7503-7592):
+ * nmat matrices, matrix m from set mat_set[m] at mat_t[m]; P_out[nmat][n][n] row-major on the host.      */
+int pb200_pmat(pb200_ctx *ctx, int n, int set_kind, int nr, int nset, long long set_stride,
+               const double *set_data, int nmat, const int *mat_set, const double *mat_t, double *P_out);
+
+/* Multi-GPU: site patterns are sharded, one context (process) per GPU, and each evaluation
+ * ends with ONE ncclAllReduce(sum) of the scalar -lnL.  Rank 0 makes an id, the launcher broadcasts the
+ * 128 bytes, every rank calls pb200_comm_init.  NCCL is dlopen'ed at the first of these calls.           */
+int pb200_nccl_unique_id(char id[128]);
+int pb200_comm_init(pb200_ctx *ctx, int nranks, int rank, const char id[128]);
+
+/* Timing / introspection for bench.py and the tests. */
+/* Device time (ms, CUDA events on the context's stream) of the last eval: [0] total, [1] P(t) kernel,
+ * [2] pruning kernel, [3] mixture/reduction kernel, [4] all-reduce.  Only filled when timing is enabled. */
+int pb200_set_timing(pb200_ctx *ctx, int enable);
+int pb200_last_timing(pb200_ctx *ctx, double ms[5]);
+/* Number of kernel launches this context has issued since creation. */
+long long pb200_launch_count(pb200_ctx *ctx);
+/* Host-side planner on its own (no GPU needed): the pruning "program" the kernel walks for this tree.
+ * Writes up to cap ints to prog; returns the number of ints needed (negative on error) and the number
+ * of on-chip slots (conditional-vector tiles live at once) in *nslots.                                   */
+int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons,
+                    const unsigned char *scale_flags, int *prog, int cap, int *nslots);
+/* FP64 peak micro-benchmark on the context's GPU: tensor (DMMA m8n8k4) and vector (DFMA) TFLOP/s.
+ * MEASURED_PEAKS.json has no FP64 figure; bench.py uses this as the FP64 roofline denominator.          */
+int pb200_measure_fp64_peak(pb200_ctx *ctx, double *dmma_tflops, double *dfma_tflops);
+/* Write `bytes` of device memory (L2 flush between timed iterations). */
+int pb200_flush_l2(pb200_ctx *ctx, long long bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAML_B200_H */

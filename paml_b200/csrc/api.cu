@@ -1,0 +1,620 @@
+// api.cu -- the C ABI of libpaml_b200.so (include/paml_b200.h): context, uploads, evaluation.
+// There is no CPU path in this library: without a usable GPU every entry point that computes fails loudly.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/paml_b200.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace pb200;
+
+static thread_local char g_err[1024] = "";
+
+static int fail(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL through dlopen (no link-time dependency; works with the system or the torch-bundled libnccl) ----
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.h) return 0;
+    const char* names[] = {getenv("PB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm) continue;
+        g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(nccl_uid_t*))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail("libnccl lacks required symbols");
+    return 0;
+}
+#define NCCL_TRY(x)                                                                                   \
+    do {                                                                                              \
+        int r_ = (x);                                                                                 \
+        if (r_ != 0) return fail("%s failed: %s", #x, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
+    } while (0)
+
+// ---- context ----
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct pb200_ctx {
+    int device = 0, nsm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    bool timing = false;
+    double last_ms[5] = {0, 0, 0, 0, 0};
+    long long launches = 0;
+    // data
+    int n = 0, ns = 0, cleandata = 1, ncodes = 0;
+    long long npatt = 0, zstride = 0;
+    DevBuf d_z, d_fpatt, d_amb_n, d_amb_map;
+    // kernel shape
+    int NT = 0, KS = 0, ld = 0;
+    long long pstride = 0;
+    // tree
+    int nnode = 0, root = -1;
+    Plan plan;
+    DevBuf d_prog;
+    // eval
+    DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush;
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    double* h_result = nullptr;
+    int last_nclass = 0;
+    bool have_eval = false;
+    // comm
+    nccl_comm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+static int ensure_host_stage(pb200_ctx* c, size_t bytes)
+{
+    if (bytes <= c->h_stage_cap) return 0;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    CUDA_TRY(cudaMallocHost(&c->h_stage, want));
+    c->h_stage_cap = want;
+    return 0;
+}
+
+extern "C" const char* pb200_last_error(void) { return g_err; }
+extern "C" const char* pb200_version(void) { return "paml_b200 0.1 (sm_100a; FP64 DMMA pruning, batched P(t), NCCL lnL all-reduce)"; }
+
+extern "C" int pb200_create(pb200_ctx** out, int device)
+{
+    if (!out) return fail("pb200_create: null out");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("pb200_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("pb200_create: device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail("pb200_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    pb200_ctx* c = new pb200_ctx();
+    c->device = device;
+    c->nsm = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_result, 64));
+    if (c->d_counter.ensure(64) || c->d_result.ensure(64)) return 1;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
+    CUDA_TRY(cudaFuncSetAttribute(pt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+extern "C" void pb200_destroy(pb200_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
+                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush};
+    for (DevBuf* b : bufs) b->release();
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static void choose_shape(int n, int* NT, int* KS)
+{
+    if (n <= 4) { *NT = 1; *KS = 1; }
+    else if (n <= 20) { *NT = 3; *KS = 5; }
+    else { *NT = 8; *KS = 16; }
+}
+
+extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, const unsigned char* z, const double* fpatt,
+                              int cleandata, const unsigned char* nchara, const unsigned char* charamap)
+{
+    if (!c) return fail("pb200_set_data: null context");
+    if (n < 2 || n > 64) return fail("pb200_set_data: n = %d unsupported (2..64)", n);
+    if (ns < 2 || npatt < 1 || !z || !fpatt) return fail("pb200_set_data: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // compact the codes in use: 0..n-1 stay, ambiguity codes (>= n) that occur are renumbered n, n+1, ...
+    int remap[256];
+    for (int i = 0; i < 256; i++) remap[i] = -1;
+    for (int i = 0; i < n; i++) remap[i] = i;
+    std::vector<unsigned char> amb_n, amb_map;
+    int ncodes = n;
+    const size_t total = (size_t)ns * npatt;
+    bool seen[256] = {false};
+    for (size_t i = 0; i < total; i++) seen[z[i]] = true;
+    for (int code = n; code < 256; code++) {
+        if (!seen[code]) continue;
+        if (!nchara || !charamap) return fail("pb200_set_data: code %d >= n but no ambiguity map given", code);
+        int cnt = nchara[code];
+        if (cnt < 1 || cnt > n) return fail("pb200_set_data: ambiguity code %d has %d states", code, cnt);
+        remap[code] = ncodes++;
+        amb_n.push_back((unsigned char)cnt);
+        for (int k = 0; k < 64; k++) {
+            unsigned char s = (k < cnt) ? charamap[code * 64 + k] : 0;
+            if (k < cnt && s >= n) return fail("pb200_set_data: ambiguity code %d maps to state %d >= n", code, (int)s);
+            amb_map.push_back(s);
+        }
+    }
+    if (ncodes > 256) return fail("pb200_set_data: too many codes");
+    long long zstride = (npatt + 127) / 128 * 128;
+    std::vector<unsigned char> zc((size_t)ns * zstride, 0);
+    for (int i = 0; i < ns; i++)
+        for (long long h = 0; h < npatt; h++) zc[(size_t)i * zstride + h] = (unsigned char)remap[z[(size_t)i * npatt + h]];
+    if (c->d_z.ensure(zc.size()) || c->d_fpatt.ensure((size_t)npatt * 8) || c->d_amb_n.ensure(amb_n.size() + 1) ||
+        c->d_amb_map.ensure(amb_map.size() + 1))
+        return 1;
+    CUDA_TRY(cudaMemcpyAsync(c->d_z.p, zc.data(), zc.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_fpatt.p, fpatt, (size_t)npatt * 8, cudaMemcpyHostToDevice, c->stream));
+    if (!amb_n.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_amb_n.p, amb_n.data(), amb_n.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_amb_map.p, amb_map.data(), amb_map.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->n = n; c->ns = ns; c->npatt = npatt; c->zstride = zstride; c->cleandata = cleandata; c->ncodes = ncodes;
+    choose_shape(n, &c->NT, &c->KS);
+    c->ld = 4 * c->KS;
+    c->pstride = std::max<long long>((long long)c->KS * c->NT * 32, (long long)ncodes * 8 * c->NT);
+    c->have_eval = false;
+    return 0;
+}
+
+extern "C" int pb200_plan_tree(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                               const unsigned char* scale_flags, int* prog, int cap, int* nslots)
+{
+    Plan pl;
+    std::string err = plan_tree(nnode, ns, root, nson, sons, maxsons, scale_flags, pl);
+    if (!err.empty()) { fail("%s", err.c_str()); return -1; }
+    if (nslots) *nslots = pl.nslots;
+    if (prog) for (int i = 0; i < cap && i < (int)pl.prog.size(); i++) prog[i] = pl.prog[i];
+    return (int)pl.prog.size();
+}
+
+extern "C" int pb200_default_scale_flags(int nnode, int root, const int* nson, const int* sons, int maxsons, int every,
+                                         unsigned char* flags)
+{
+    // SetNodeScale (src/treesub.c:7178-7198) without recursion: d(v) = number of tips below v, counted
+    // post-order; a non-root node with d > every is flagged and then counts as 1 for its ancestors.
+    std::vector<int> d(nnode, 0);
+    std::vector<std::pair<int, int>> st;
+    int count = 0;
+    memset(flags, 0, nnode);
+    st.push_back({root, 0});
+    while (!st.empty()) {
+        int v = st.back().first, k = st.back().second;
+        if (k < nson[v]) {
+            st.back().second++;
+            int s = sons[v * maxsons + k];
+            if (nson[s] > 0) st.push_back({s, 0});
+            else d[s] = 1;
+        }
+        else {
+            int t = 0;
+            for (int j = 0; j < nson[v]; j++) t += d[sons[v * maxsons + j]];
+            if (v != root && t > every) { flags[v] = 1; t = 1; count++; }
+            d[v] = t;
+            st.pop_back();
+        }
+    }
+    return count;
+}
+
+extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson, const int* sons, int maxsons,
+                              const unsigned char* scale_flags)
+{
+    if (!c) return fail("pb200_set_tree: null context");
+    if (c->ns == 0) return fail("pb200_set_tree: call pb200_set_data first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Plan pl;
+    std::string err = plan_tree(nnode, c->ns, root, nson, sons, maxsons, scale_flags, pl);
+    if (!err.empty()) return fail("%s", err.c_str());
+    if (c->d_prog.ensure(pl.prog.size() * sizeof(int))) return 1;
+    CUDA_TRY(cudaMemcpyAsync(c->d_prog.p, pl.prog.data(), pl.prog.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->plan = pl; c->nnode = nnode; c->root = root;
+    c->have_eval = false;
+    return 0;
+}
+
+// ---- pruning kernel dispatch ----
+struct PruneLaunch {
+    void (*fn)(const PruneParams);
+    int rows, slot_doubles, max_warps;
+};
+template <int NT, int KS, int MT, int MAXW>
+static PruneLaunch make_launch()
+{
+    PruneLaunch L;
+    L.fn = prune_kernel<NT, KS, MT, MAXW>;
+    L.rows = PruneCfg<NT, KS, MT>::ROWS;
+    L.slot_doubles = PruneCfg<NT, KS, MT>::SLOT_DOUBLES;
+    L.max_warps = MAXW;
+    return L;
+}
+static int pick_launch(int NT, int mt_small, PruneLaunch* L)
+{
+    if (NT == 8) *L = mt_small ? make_launch<8, 16, 1, 8>() : make_launch<8, 16, 2, 8>();
+    else if (NT == 3) *L = mt_small ? make_launch<3, 5, 1, 16>() : make_launch<3, 5, 2, 16>();
+    else if (NT == 1) *L = mt_small ? make_launch<1, 1, 1, 16>() : make_launch<1, 1, 4, 16>();
+    else return fail("no pruning kernel for NT = %d", NT);
+    return 0;
+}
+
+static size_t smem_budget()
+{
+    const char* e = getenv("PB200_SMEM_KB");
+    long kb = e ? atol(e) : 160;
+    if (kb < 8) kb = 8;
+    if (kb > 227) kb = 227;
+    return (size_t)kb * 1024;
+}
+
+static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    PruneLaunch L;
+    int warps = 0;
+    size_t per_warp = 0;
+    for (int small = 0; small < 2 && warps == 0; small++) {
+        if (pick_launch(c->NT, small, &L)) return 1;
+        per_warp = (size_t)c->plan.nslots * L.slot_doubles * sizeof(double);
+        size_t budget = smem_budget();
+        warps = (int)std::min<size_t>(L.max_warps, budget / per_warp);
+        if (warps == 0 && small == 1) warps = (int)std::min<size_t>(L.max_warps, (size_t)227 * 1024 / per_warp);
+    }
+    if (warps == 0) return fail("tree needs %d on-chip slots of %d doubles per warp: does not fit in shared memory", c->plan.nslots, L.slot_doubles);
+    const char* wenv = getenv("PB200_WARPS");
+    if (wenv && atoi(wenv) > 0) warps = std::min(warps, atoi(wenv));
+    size_t smem = per_warp * warps;
+    CUDA_TRY(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PruneParams p;
+    p.prog = (const int*)c->d_prog.p;
+    p.z = (const unsigned char*)c->d_z.p;
+    p.zstride = c->zstride; p.npatt = c->npatt;
+    p.ntiles = (c->npatt + L.rows - 1) / L.rows;
+    p.nitems = p.ntiles * nclass;
+    p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
+    p.nnode = c->nnode; p.nclass = nclass; p.nslots = c->plan.nslots; p.n = c->n;
+    p.semantics = semantics; p.nscale = c->plan.nscale;
+    p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, L.fn, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long want = (p.nitems + warps - 1) / warps;
+    int grid = (int)std::min<long long>(want, (long long)c->nsm * per_sm);
+    if (grid < 1) grid = 1;
+    L.fn<<<grid, warps * 32, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride, const double* d_sets, int nmat,
+                     const int* d_mat_set, const double* d_mat_t, double* d_out, long long pstride, int mode, int nnode, int ns,
+                     int NT, int KS, int ncodes)
+{
+    PtParams p;
+    p.n = n; p.NT = NT; p.KS = KS; p.ld = 4 * KS; p.ncodes = ncodes; p.ns = ns; p.nnode = nnode;
+    p.kind = kind; p.nr = nr; p.set_stride = set_stride; p.sets = d_sets; p.mat_set = d_mat_set; p.mat_t = d_mat_t;
+    p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
+    p.out = d_out; p.pstride = pstride; p.mode = mode;
+    size_t smem = (size_t)(kind == KIND_UVROOT ? 2 : 1) * p.ld * p.ld * sizeof(double);
+    pt_kernel<<<nmat, 256, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+static int check_sets(int n, int set_kind, int nr, int nset, long long set_stride)
+{
+    if (nset < 1) return fail("nset < 1");
+    long long need = 0;
+    switch (set_kind) {
+    case KIND_UVROOT: need = (long long)n + 2LL * n * n; break;
+    case KIND_CIJK:
+        if (nr < 1 || nr > 8) return fail("CIJK sets need 1 <= nr <= 8");
+        need = (long long)nr + (long long)n * n * nr;
+        break;
+    case KIND_K80:
+        if (n != 4) return fail("K80 sets need n = 4");
+        need = 1;
+        break;
+    case KIND_JC69LIKE: need = 0; break;
+    default: return fail("unknown set_kind %d", set_kind);
+    }
+    if (set_stride < need) return fail("set_stride %lld too small for kind %d (need %lld)", set_stride, set_kind, need);
+    return 0;
+}
+
+extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double* freqK, int set_kind, int nr, int nset,
+                          long long set_stride, const double* set_data, const int* branch_set, const double* branch_t,
+                          const double* pi, double* neg_lnL)
+{
+    if (!c) return fail("pb200_eval: null context");
+    if (c->npatt == 0 || c->nnode == 0) return fail("pb200_eval: set_data and set_tree must be called first");
+    if (semantics != SEM_LFUN && semantics != SEM_LFUNDG) return fail("pb200_eval: bad semantics");
+    if (nclass < 1 || (semantics == SEM_LFUN && nclass != 1)) return fail("pb200_eval: bad nclass %d", nclass);
+    if (!freqK || !branch_set || !branch_t || !pi || !neg_lnL) return fail("pb200_eval: null argument");
+    if (check_sets(c->n, set_kind, nr, nset, set_stride)) return 1;
+    if (set_stride > 0 && !set_data) return fail("pb200_eval: null set_data");
+    const int nnode = c->nnode, n = c->n, NP = 8 * c->NT;
+    const int nmat = nclass * nnode;
+    for (int m = 0; m < nmat; m++) {
+        int node = m % nnode;
+        if (node == c->root) continue;
+        if (branch_set[m] < 0 || branch_set[m] >= nset) return fail("pb200_eval: branch_set[%d] = %d out of range", m, branch_set[m]);
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    // one pinned staging block -> one H2D copy: freqK | pi (padded) | sets | branch_t | branch_set
+    size_t off_freq = 0;
+    size_t off_pi = align16(off_freq + (size_t)nclass * 8);
+    size_t off_sets = align16(off_pi + (size_t)NP * 8);
+    size_t off_t = align16(off_sets + (size_t)nset * set_stride * 8);
+    size_t off_set = align16(off_t + (size_t)nmat * 8);
+    size_t total = align16(off_set + (size_t)nmat * 4);
+    if (ensure_host_stage(c, total) || c->d_stage.ensure(total)) return 1;
+    char* hs = (char*)c->h_stage;
+    memcpy(hs + off_freq, freqK, (size_t)nclass * 8);
+    memset(hs + off_pi, 0, (size_t)NP * 8);
+    memcpy(hs + off_pi, pi, (size_t)n * 8);
+    if (set_stride > 0) memcpy(hs + off_sets, set_data, (size_t)nset * set_stride * 8);
+    memcpy(hs + off_t, branch_t, (size_t)nmat * 8);
+    {
+        int* bs = (int*)(hs + off_set);
+        for (int m = 0; m < nmat; m++) bs[m] = (m % nnode == c->root) ? -1 : branch_set[m];
+    }
+    if (c->d_P.ensure((size_t)nmat * c->pstride * 8) || c->d_fhK.ensure((size_t)nclass * c->npatt * 8) ||
+        c->d_lnf.ensure((size_t)c->npatt * 8))
+        return 1;
+    int mix_blocks = (int)std::min<long long>((c->npatt + 255) / 256, 2LL * c->nsm);
+    if (c->d_partial.ensure((size_t)mix_blocks * 8)) return 1;
+
+    char* ds = (char*)c->d_stage.p;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, c->stream));
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
+                  (const double*)(ds + off_t), (double*)c->d_P.p, c->pstride, PT_MODE_AUTO, nnode, c->ns, c->NT, c->KS, c->ncodes))
+        return 1;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (launch_prune(c, nclass, semantics, (const double*)(ds + off_pi))) return 1;
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    {
+        MixParams mp;
+        mp.fhK = (const double*)c->d_fhK.p; mp.fpatt = (const double*)c->d_fpatt.p; mp.freqK = (const double*)(ds + off_freq);
+        mp.lnf = (double*)c->d_lnf.p; mp.partial = (double*)c->d_partial.p; mp.counter = (unsigned int*)c->d_counter.p;
+        mp.result = (double*)c->d_result.p; mp.npatt = c->npatt; mp.nclass = nclass; mp.semantics = semantics;
+        mp.nscale = c->plan.nscale;
+        mix_kernel<<<mix_blocks, 256, 0, c->stream>>>(mp);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    if (c->comm && c->nranks > 1)
+        NCCL_TRY(g_nccl.AllReduce(c->d_result.p, c->d_result.p, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *neg_lnL = c->h_result[0];
+    c->last_nclass = nclass;
+    c->have_eval = true;
+    if (c->timing) {
+        float ms;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); c->last_ms[0] = ms;
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[2] = ms;
+        cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->last_ms[3] = ms;
+        cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->last_ms[4] = ms;
+    }
+    return 0;
+}
+
+extern "C" int pb200_get_lnf(pb200_ctx* c, double* lnf)
+{
+    if (!c || !lnf) return fail("pb200_get_lnf: null argument");
+    if (!c->have_eval) return fail("pb200_get_lnf: no evaluation yet");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(lnf, c->d_lnf.p, (size_t)c->npatt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int pb200_get_fhK(pb200_ctx* c, double* fhK)
+{
+    if (!c || !fhK) return fail("pb200_get_fhK: null argument");
+    if (!c->have_eval) return fail("pb200_get_fhK: no evaluation yet");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(fhK, c->d_fhK.p, (size_t)c->last_nclass * c->npatt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int pb200_pmat(pb200_ctx* c, int n, int set_kind, int nr, int nset, long long set_stride, const double* set_data,
+                          int nmat, const int* mat_set, const double* mat_t, double* P_out)
+{
+    if (!c) return fail("pb200_pmat: null context");
+    if (n < 2 || n > 64 || nmat < 1 || !mat_set || !mat_t || !P_out) return fail("pb200_pmat: bad arguments");
+    if (check_sets(n, set_kind, nr, nset, set_stride)) return 1;
+    for (int m = 0; m < nmat; m++)
+        if (mat_set[m] < 0 || mat_set[m] >= nset) return fail("pb200_pmat: mat_set[%d] out of range", m);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int NT, KS;
+    choose_shape(n, &NT, &KS);
+    DevBuf d_sets, d_ms, d_mt, d_out;
+    size_t sb = (size_t)std::max<long long>(1, (long long)nset * set_stride) * 8;
+    if (d_sets.ensure(sb) || d_ms.ensure((size_t)nmat * 4) || d_mt.ensure((size_t)nmat * 8) || d_out.ensure((size_t)nmat * n * n * 8))
+        return 1;
+    int rc = 0;
+    do {
+        if (set_stride > 0 && cudaMemcpyAsync(d_sets.p, set_data, (size_t)nset * set_stride * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail("pb200_pmat: H2D failed"); break; }
+        if (cudaMemcpyAsync(d_ms.p, mat_set, (size_t)nmat * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail("pb200_pmat: H2D failed"); break; }
+        if (cudaMemcpyAsync(d_mt.p, mat_t, (size_t)nmat * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail("pb200_pmat: H2D failed"); break; }
+        rc = launch_pt(c, n, set_kind, nr, set_stride, (const double*)d_sets.p, nmat, (const int*)d_ms.p, (const double*)d_mt.p,
+                       (double*)d_out.p, (long long)n * n, PT_MODE_PLAIN, 1, 0, NT, KS, n);
+        if (rc) break;
+        if (cudaMemcpyAsync(P_out, d_out.p, (size_t)nmat * n * n * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = fail("pb200_pmat: D2H failed"); break; }
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail("pb200_pmat: %s", cudaGetErrorString(e));
+    } while (0);
+    d_sets.release(); d_ms.release(); d_mt.release(); d_out.release();
+    return rc;
+}
+
+extern "C" int pb200_nccl_unique_id(char id[128])
+{
+    if (nccl_load()) return 1;
+    nccl_uid_t u;
+    NCCL_TRY(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+extern "C" int pb200_comm_init(pb200_ctx* c, int nranks, int rank, const char id[128])
+{
+    if (!c) return fail("pb200_comm_init: null context");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("pb200_comm_init: bad rank %d / %d", rank, nranks);
+    if (nccl_load()) return 1;
+    CUDA_TRY(cudaSetDevice(c->device));
+    nccl_uid_t u;
+    memcpy(u.internal, id, 128);
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    c->nranks = nranks; c->rank = rank;
+    return 0;
+}
+
+extern "C" int pb200_set_timing(pb200_ctx* c, int enable)
+{
+    if (!c) return fail("pb200_set_timing: null context");
+    c->timing = (enable != 0);
+    return 0;
+}
+
+extern "C" int pb200_last_timing(pb200_ctx* c, double ms[5])
+{
+    if (!c || !ms) return fail("pb200_last_timing: null argument");
+    for (int i = 0; i < 5; i++) ms[i] = c->last_ms[i];
+    return 0;
+}
+
+extern "C" long long pb200_launch_count(pb200_ctx* c) { return c ? c->launches : -1; }
+
+extern "C" int pb200_measure_fp64_peak(pb200_ctx* c, double* dmma_tflops, double* dfma_tflops)
+{
+    if (!c) return fail("pb200_measure_fp64_peak: null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int threads = 256, iters = 20000;
+    DevBuf out;
+    if (out.ensure((size_t)c->nsm * threads * 8)) return 1;
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; which++) {
+        for (int rep = 0; rep < 5; rep++) {
+            CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+            if (which == 0) peak_dmma_kernel<<<c->nsm, threads, 0, c->stream>>>((double*)out.p, iters, 1.0000001, 1e-9);
+            else            peak_dfma_kernel<<<c->nsm, threads, 0, c->stream>>>((double*)out.p, iters, 1.0000001, 1e-9);
+            c->launches++;
+            CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            float ms;
+            CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+            double flop = (which == 0) ? (double)c->nsm * (threads / 32) * iters * 8 * (8.0 * 8 * 4 * 2)
+                                       : (double)c->nsm * threads * iters * 16 * 2.0;
+            double tf = flop / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best[which]) best[which] = tf;
+        }
+    }
+    out.release();
+    if (dmma_tflops) *dmma_tflops = best[0];
+    if (dfma_tflops) *dfma_tflops = best[1];
+    return 0;
+}
+
+extern "C" int pb200_flush_l2(pb200_ctx* c, long long bytes)
+{
+    if (!c) return fail("pb200_flush_l2: null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (bytes < 8) bytes = 8;
+    if (c->d_flush.ensure((size_t)bytes)) return 1;
+    flush_kernel<<<c->nsm * 4, 256, 0, c->stream>>>((double*)c->d_flush.p, bytes / 8, 1.0);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

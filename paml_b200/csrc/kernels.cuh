@@ -1,0 +1,471 @@
+// kernels.cuh -- hand-written sm_100a kernels of the PAML tree-likelihood hot path.
+//
+//   pt_kernel      batched P(t) for every (site class, branch): replaces PMatUVRoot (src/tools.c:516-546),
+//                  PMatCijk (src/baseml.c:1572-1589), PMatK80 (src/tools.c:578-606), PMatJC69like
+//                  (src/codeml.c:3585-3594) as selected by GetPMatBranch (src/treesub.c:7503-7592).
+//   prune_kernel   Felsenstein pruning of whole trees, replaces ConditionalPNode (src/codeml.c:3526-3582,
+//                  src/baseml.c:1517-1570) + NodeScale (src/treesub.c:7200-7230) + the root pi-dot of
+//                  lfun / fx_r (src/treesub.c:7780-7798, 7726-7750).
+//   mix_kernel     class mixture, weighting and deterministic sum: the h-loops of lfun
+//                  (src/treesub.c:7778-7804) and lfundG (src/treesub.c:7630-7657).
+//
+// All arithmetic is IEEE double.  The state x state contraction at internal nodes runs on the FP64 tensor
+// path (DMMA, mma.sync.m8n8k4.f64 -- the only FP64 MMA shape sm_100a executes natively; tcgen05 has no
+// FP64 kind).  See DESIGN.md for layouts and rooflines.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "plan.h"
+
+namespace pb200 {
+
+enum { KIND_UVROOT = 0, KIND_CIJK = 1, KIND_K80 = 2, KIND_JC69LIKE = 3 };
+enum { SEM_LFUN = 0, SEM_LFUNDG = 1 };
+enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// P(t)
+// ------------------------------------------------------------------------------------------------
+struct PtParams {
+    int n;              // states
+    int ld;             // n rounded up to a multiple of 4 (= 4*KS): leading dimension in shared memory
+    int NT, KS;         // n-tiles (8 output states) / k-steps (4 input states) of the pruning kernel
+    int ncodes;         // n + number of ambiguity codes in use (rows of a tip matrix)
+    int ns, nnode;      // matrix m belongs to node m % nnode; tips are nodes < ns
+    int kind, nr;
+    long long set_stride;
+    const double* sets; // [nset][set_stride]
+    const int* mat_set; // [nmat] (-1 = skip)
+    const double* mat_t;// [nmat]
+    const unsigned char* amb_n;    // [ncodes - n]
+    const unsigned char* amb_map;  // [ncodes - n][64]
+    double* out;        // [nmat][pstride]
+    long long pstride;
+    int mode;           // PT_MODE_*
+};
+
+// One CTA (256 threads) per matrix.  Shared memory: 2*ld*ld doubles (UVROOT) or ld*ld (other kinds).
+__global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int m = blockIdx.x, tid = threadIdx.x, n = p.n, ld = p.ld;
+    const int iset = p.mat_set[m];
+    if (iset < 0) return;                                   // the root has no branch
+    const double t = p.mat_t[m];
+    const double* set = p.sets + (size_t)iset * p.set_stride;
+    double* Psm = sm;                                       // [ld][ld] result, row-major P[i][j]
+
+    if (p.kind == KIND_UVROOT && !(t < 1e-100)) {
+        // P = I + sum_k U[:,k] expm1(t Root[k]) V[k,:]   (src/tools.c:529-534)
+        const double *Root = set, *U = set + n, *V = set + n + (size_t)n * n;
+        double* Ue = sm;                 // [ld][ld]  U[i][k] * expm1(t*Root[k])
+        double* Vs = sm + ld * ld;       // [ld][ld]
+        for (int e = tid; e < ld * ld; e += 256) {
+            int i = e / ld, k = e - i * ld;
+            bool ok = (i < n && k < n);
+            Ue[e] = ok ? U[i * n + k] * expm1(t * Root[k]) : 0.0;
+            Vs[e] = ok ? V[i * n + k] : 0.0;
+        }
+        __syncthreads();
+        const int ty = tid >> 4, tx = tid & 15;
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
+        const bool active = (ty < ld && tx < ld);
+        if (active) {
+            for (int k = 0; k < n; k++) {
+                double u[4], v[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) { int i = ty + 16 * r; u[r] = (i < ld) ? Ue[i * ld + k] : 0.0; }
+#pragma unroll
+                for (int c = 0; c < 4; c++) { int j = tx + 16 * c; v[c] = (j < ld) ? Vs[k * ld + j] : 0.0; }
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] = fma(u[r], v[c], acc[r][c]);
+            }
+        }
+        __syncthreads();                 // everyone is done reading Ue/Vs before Psm (= Ue) is overwritten
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int i = ty + 16 * r, j = tx + 16 * c;
+                    if (i < ld && j < ld) {
+                        double v = acc[r][c] + (i == j ? 1.0 : 0.0);
+                        if (v < 0) v = 0;                   // src/tools.c:536-537
+                        Psm[i * ld + j] = (i < n && j < n) ? v : 0.0;
+                    }
+                }
+        }
+    }
+    else {
+        double e1 = 0, e2 = 0, ex[8];
+        if (p.kind == KIND_K80) {                           // src/tools.c:588-603
+            double kappa = set[0];
+            e1 = expm1(-4 * t / (kappa + 2));
+            e2 = expm1(-2 * t * (kappa + 1) / (kappa + 2));
+        }
+        else if (p.kind == KIND_CIJK) {                     // src/baseml.c:1580
+            ex[0] = 0;
+            for (int k = 1; k < p.nr && k < 8; k++) ex[k] = expm1(t * set[k]);
+        }
+        else if (p.kind == KIND_JC69LIKE) {                 // src/codeml.c:3588-3589
+            e1 = 1. / n + (1. - 1. / n) * exp(-n / (n - 1.) * t);
+            e2 = (1. - e1) / (n - 1.);
+        }
+        for (int e = tid; e < ld * ld; e += 256) {
+            int i = e / ld, j = e - i * ld;
+            double v = 0;
+            if (i < n && j < n) {
+                if (p.kind == KIND_UVROOT) v = (i == j);    // t < 1e-100 -> identity (src/tools.c:525-528)
+                else if (p.kind == KIND_K80) {
+                    double kappa = set[0];
+                    if (fabs(kappa - 1) < 1e-20) v = (i == j ? 1. + 3 / 4.0 * e1 : -e1 / 4);
+                    else if (i == j)             v = 1 + (e1 + 2 * e2) / 4;
+                    else if ((i ^ j) == 1)       v = (e1 - 2 * e2) / 4;
+                    else                         v = -e1 / 4;
+                }
+                else if (p.kind == KIND_CIJK) {
+                    const double* C = set + p.nr + ((size_t)i * n + j) * p.nr;
+                    for (int k = 0; k < p.nr; k++) v += C[k] * ex[k];
+                    if (i == j) v += 1;
+                }
+                else v = (i == j ? e1 : e2);
+            }
+            Psm[e] = v;
+        }
+    }
+    __syncthreads();
+
+    // write the matrix in the layout its consumer wants
+    double* out = p.out + (size_t)m * p.pstride;
+    const int node = m % p.nnode;
+    const int mode = (p.mode != PT_MODE_AUTO) ? p.mode : (node < p.ns ? PT_MODE_TIP : PT_MODE_FRAG);
+    const int NP = 8 * p.NT;
+    if (mode == PT_MODE_PLAIN) {
+        for (int e = tid; e < n * n; e += 256) { int i = e / n, j = e - i * n; out[e] = Psm[i * ld + j]; }
+    }
+    else if (mode == PT_MODE_TIP) {
+        // PT[code][j] = sum_{k in code} P[j][k]: what a tip in state `code` contributes to parent state j
+        // (src/codeml.c:3555-3567); padded parent states j >= n get 0.
+        for (int e = tid; e < p.ncodes * NP; e += 256) {
+            int code = e / NP, j = e - code * NP;
+            double v = 0;
+            if (j < n) {
+                if (code < n) v = Psm[j * ld + code];
+                else {
+                    const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
+                    int cnt = p.amb_n[code - n];
+                    for (int k = 0; k < cnt; k++) v += Psm[j * ld + mp[k]];
+                }
+            }
+            out[e] = v;
+        }
+    }
+    else {
+        // DMMA B-fragment order: element (ks, nt, lane) = P[8nt + lane/4][4ks + lane%4]
+        const int total = p.KS * p.NT * 32;
+        for (int e = tid; e < total; e += 256) {
+            int lane = e & 31, f = e >> 5, nt = f % p.NT, ks = f / p.NT;
+            int j = 8 * nt + (lane >> 2), k = 4 * ks + (lane & 3);
+            out[e] = (j < n && k < n) ? Psm[j * ld + k] : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pruning
+// ------------------------------------------------------------------------------------------------
+struct PruneParams {
+    const int* prog;            // plan.h program
+    const unsigned char* z;     // [ns][zstride] compact codes
+    long long zstride, npatt, ntiles, nitems;
+    const double* Pbuf;         // [nclass][nnode][pstride]
+    long long pstride;
+    int nnode, nclass, nslots, n, semantics, nscale;
+    const double* pi;           // [8*NT] zero padded
+    double* fhK;                // [nclass][npatt]
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NT, int KS, int MT>
+struct PruneCfg {
+    static constexpr int NP = 8 * NT;                       // padded output states
+    static constexpr int KP = 4 * KS;                       // padded input states
+    // row stride of a slot: conflict-free A-fragment loads need stride % 16 in {4, 12}
+    static constexpr int STRIDE = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;
+    static constexpr int ROWS = 8 * MT;                     // patterns per warp
+    static constexpr int SLOT_DOUBLES = ROWS * STRIDE;
+};
+
+// One warp owns ROWS site patterns of one site class and walks the whole tree for them; conditional
+// vectors stay in registers (the node being built, C-fragment layout) and in the warp's private shared
+// memory slots (finished children, [pattern][state] rows).  No block-level synchronisation at all.
+template <int NT, int KS, int MT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams p)
+{
+    using C = PruneCfg<NT, KS, MT>;
+    extern __shared__ __align__(16) double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;   // nw <= WARPS
+    const int g = lane >> 2, q = lane & 3;
+    double* slots = sm + (size_t)warp * p.nslots * C::SLOT_DOUBLES;
+    const long long N = p.npatt;
+
+    for (long long item = (long long)blockIdx.x * nw + warp; item < p.nitems; item += (long long)gridDim.x * nw) {
+        const int cls = (int)(item / p.ntiles);
+        const long long h0 = (item - (long long)cls * p.ntiles) * C::ROWS;
+        const double* Pcls = p.Pbuf + (size_t)cls * p.nnode * p.pstride;
+        double lnsc[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) lnsc[mt] = 0.0;
+
+        const int* pc = p.prog + 2;
+        const int nops = p.prog[0];
+        for (int op = 0; op < nops; op++) {
+            const int nchild = pc[0], out_slot = pc[1], sidx = pc[2];
+            pc += OP_HDR;
+            double acc[MT][NT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 1.0;
+
+            for (int c = 0; c < nchild; c++) {
+                const int kind = pc[0], idx = pc[1], node = pc[2];
+                pc += CH_REC;
+                const double* Pm = Pcls + (size_t)node * p.pstride;
+                if (kind == CH_TIP) {
+                    // acc[h][j] *= PT[z_h][j]                          (src/codeml.c:3555-3567)
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        long long h = h0 + 8 * mt + g;
+                        int code = (h < N) ? (int)p.z[(size_t)idx * p.zstride + h] : 0;
+                        const double2* row = reinterpret_cast<const double2*>(Pm + (size_t)code * C::NP);
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            double2 v = __ldg(row + nt * 4 + q);
+                            acc[mt][nt][0] *= v.x; acc[mt][nt][1] *= v.y;
+                        }
+                    }
+                }
+                else if (kind == CH_INTERNAL) {
+                    // acc[h][j] *= sum_k P[j][k] L_child[h][k]           (src/codeml.c:3568-3575) on DMMA
+                    const double* S = slots + (size_t)idx * C::SLOT_DOUBLES;
+                    double tmp[MT][NT][2];
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) tmp[mt][nt][0] = tmp[mt][nt][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) {
+                        double a[MT], b[NT];
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) a[mt] = S[(8 * mt + g) * C::STRIDE + 4 * ks + q];
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) b[nt] = __ldg(Pm + (ks * NT + nt) * 32 + lane);
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                            for (int mt = 0; mt < MT; mt++) dmma884(tmp[mt][nt][0], tmp[mt][nt][1], a[mt], b[nt]);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] *= tmp[mt][nt][0]; acc[mt][nt][1] *= tmp[mt][nt][1]; }
+                }
+                else {
+                    // running product of a folded multifurcation, stored earlier in C-fragment positions
+                    const double* S = slots + (size_t)idx * C::SLOT_DOUBLES;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            if (8 * nt + 2 * q < C::KP) {
+                                double2 v = *reinterpret_cast<const double2*>(S + (8 * mt + g) * C::STRIDE + 8 * nt + 2 * q);
+                                acc[mt][nt][0] *= v.x; acc[mt][nt][1] *= v.y;
+                            }
+                        }
+                }
+            }
+
+            if (sidx >= 0) {
+                // NodeScale (src/treesub.c:7213-7227): divide by the per-pattern maximum, remember its log
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    double mx = 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) { mx = fmax(mx, acc[mt][nt][0]); mx = fmax(mx, acc[mt][nt][1]); }
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    if (mx < 1e-300) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            acc[mt][nt][0] = (8 * nt + 2 * q     < p.n) ? 1.0 : 0.0;
+                            acc[mt][nt][1] = (8 * nt + 2 * q + 1 < p.n) ? 1.0 : 0.0;
+                        }
+                        lnsc[mt] += -800.0;
+                    }
+                    else {
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] /= mx; acc[mt][nt][1] /= mx; }
+                        lnsc[mt] += log(mx);
+                    }
+                }
+            }
+
+            if (out_slot >= 0) {
+                double* S = slots + (size_t)out_slot * C::SLOT_DOUBLES;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++)
+                        if (8 * nt + 2 * q < C::KP)
+                            *reinterpret_cast<double2*>(S + (8 * mt + g) * C::STRIDE + 8 * nt + 2 * q) =
+                                make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                __syncwarp();
+            }
+            else {
+                // root: f_h = sum_i pi_i L_root[h][i]  (src/treesub.c:7780-7781, 7728-7729), then the
+                // guards and scale factors of lfun (7782-7798) or fx_r (7731-7750)
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    double fh = 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) {
+                        double2 w = __ldg(reinterpret_cast<const double2*>(p.pi) + nt * 4 + q);
+                        fh = fma(w.x, acc[mt][nt][0], fh);
+                        fh = fma(w.y, acc[mt][nt][1], fh);
+                    }
+                    fh += __shfl_xor_sync(0xffffffffu, fh, 1);
+                    fh += __shfl_xor_sync(0xffffffffu, fh, 2);
+                    long long h = h0 + 8 * mt + g;
+                    if (q == 0 && h < N) {
+                        double v;
+                        if (p.semantics == SEM_LFUN) {
+                            if (fh <= 0) fh = 1e-80;
+                            v = log(fh) + lnsc[mt];
+                        }
+                        else {
+                            if (fh <= 0) fh = 1e-300;
+                            v = p.nscale ? log(fh) + lnsc[mt] : fh;
+                        }
+                        p.fhK[(size_t)cls * N + h] = v;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mixture + weighted deterministic sum
+// ------------------------------------------------------------------------------------------------
+struct MixParams {
+    const double* fhK;      // [nclass][npatt]
+    const double* fpatt;    // [npatt]
+    const double* freqK;    // [nclass]
+    double* lnf;            // [npatt] out
+    double* partial;        // [gridDim.x] scratch
+    unsigned int* counter;  // zero-initialised, reset by the last block
+    double* result;         // [1] out: -lnL of this shard
+    long long npatt;
+    int nclass, semantics, nscale;
+};
+
+// Block b sums patterns [b*chunk, (b+1)*chunk) in a fixed order; the last block to finish adds the block
+// partials in index order.  No floating-point atomics anywhere, so -lnL(x) is reproducible call to call
+// (the optimiser differentiates it numerically, src/tools.c:6561-6590).
+__global__ void __launch_bounds__(256) mix_kernel(const MixParams p)
+{
+    __shared__ double red[256];
+    __shared__ bool last;
+    const int tid = threadIdx.x;
+    const long long N = p.npatt;
+    double s = 0.0;
+    for (long long h = (long long)blockIdx.x * 256 + tid; h < N; h += (long long)gridDim.x * 256) {
+        double w = p.fpatt[h], fh;
+        if (w <= 0) { p.lnf[h] = 0.0; continue; }           // src/treesub.c:7779, 7631
+        if (p.semantics == SEM_LFUN) fh = p.fhK[h];
+        else if (p.nscale) {                                 // src/treesub.c:7632-7638
+            int it = 0;
+            for (int ir = 1; ir < p.nclass; ir++) if (p.fhK[(size_t)ir * N + h] > p.fhK[(size_t)it * N + h]) it = ir;
+            double t = p.fhK[(size_t)it * N + h];
+            fh = 0.0;
+            for (int ir = 0; ir < p.nclass; ir++) fh += p.freqK[ir] * exp(p.fhK[(size_t)ir * N + h] - t);
+            fh = t + log(fh);
+        }
+        else {                                               // src/treesub.c:7640-7652
+            fh = 0.0;
+            for (int ir = 0; ir < p.nclass; ir++) fh += p.freqK[ir] * p.fhK[(size_t)ir * N + h];
+            if (fh <= 0) fh = 1e-300;
+            fh = log(fh);
+        }
+        p.lnf[h] = fh;
+        s -= fh * w;
+    }
+    red[tid] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
+    if (tid == 0) {
+        p.partial[blockIdx.x] = red[0];
+        __threadfence();
+        unsigned int done = atomicAdd(p.counter, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t = 0.0;
+        for (int b = tid; b < (int)gridDim.x; b += 256) t += p.partial[b];
+        red[tid] = t;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
+        if (tid == 0) { p.result[0] = red[0]; *p.counter = 0u; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak micro-benchmarks (roofline denominators) and L2 flush
+// ------------------------------------------------------------------------------------------------
+__global__ void peak_dmma_kernel(double* out, int iters, double a, double b)
+{
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = threadIdx.x; }
+    for (int it = 0; it < iters; it++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], a, b);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void peak_dfma_kernel(double* out, int iters, double a, double b)
+{
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; it++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i] = fma(c[i], a, b);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void flush_kernel(double* buf, long long n, double v)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) buf[i] = v;
+}
+
+}  // namespace pb200

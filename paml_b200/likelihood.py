@@ -1,0 +1,169 @@
+"""Python mirror of the drop-in boundary: one object per (data set, tree) whose ``eval`` is one call of the
+reference's ``com.plfun`` (lfun / lfundG, src/treesub.c:7764 / 7608) on the GPU.
+
+It is a thin ctypes layer over the C ABI (include/paml_b200.h): the same calls the C host shim
+(paml_b200/host/plfun_b200.inc) makes from inside codeml/baseml.  Used by the tests, bench.py and smoke().
+"""
+import ctypes as C
+import numpy as np
+
+from ._lib import lib, check, PB200Error  # noqa: F401
+from .fixture import Problem, SEM_LFUN, SEM_LFUNDG  # noqa: F401
+
+
+def _ptr(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def plan_tree(nnode, ns, root, nson, sons, scale_flags=None):
+    """Host-side planner only (no GPU): returns (program int32 array, nslots)."""
+    L = lib()
+    nson = np.ascontiguousarray(nson, np.int32)
+    sons = np.ascontiguousarray(sons, np.int32)
+    maxsons = sons.shape[1]
+    flags = None if scale_flags is None else np.ascontiguousarray(scale_flags, np.uint8)
+    nslots = C.c_int(0)
+    need = L.pb200_plan_tree(C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
+                             C.c_int(maxsons), _ptr(flags, C.c_ubyte), None, C.c_int(0), C.byref(nslots))
+    if need < 0:
+        raise PB200Error(L.pb200_last_error().decode())
+    prog = np.zeros(need, np.int32)
+    L.pb200_plan_tree(C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
+                      C.c_int(maxsons), _ptr(flags, C.c_ubyte), _ptr(prog, C.c_int), C.c_int(need), C.byref(nslots))
+    return prog, nslots.value
+
+
+def default_scale_flags(nnode, root, nson, sons, every):
+    nson = np.ascontiguousarray(nson, np.int32)
+    sons = np.ascontiguousarray(sons, np.int32)
+    flags = np.zeros(nnode, np.uint8)
+    k = lib().pb200_default_scale_flags(C.c_int(nnode), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
+                                        C.c_int(sons.shape[1]), C.c_int(every), _ptr(flags, C.c_ubyte))
+    return k, flags
+
+
+class TreeLikelihood:
+    """GPU tree-likelihood context for one shard of site patterns on one device."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        self._ctx = C.c_void_p()
+        check(self._L.pb200_create(C.byref(self._ctx), C.c_int(device)))
+        self.npatt = 0
+        self.nclass = 1
+        self.nnode = 0
+
+    def close(self):
+        if self._ctx:
+            self._L.pb200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- static part ------------------------------------------------------------------------------
+    def set_data(self, n, z, fpatt, cleandata=1, nchara=None, charamap=None):
+        z = np.ascontiguousarray(z, np.uint8)
+        fpatt = np.ascontiguousarray(fpatt, np.float64)
+        ns, npatt = z.shape
+        assert fpatt.shape == (npatt,)
+        nchara = None if nchara is None else np.ascontiguousarray(nchara, np.uint8)
+        charamap = None if charamap is None else np.ascontiguousarray(charamap, np.uint8)
+        check(self._L.pb200_set_data(self._ctx, C.c_int(n), C.c_int(ns), C.c_longlong(npatt), _ptr(z, C.c_ubyte),
+                                     _ptr(fpatt, C.c_double), C.c_int(cleandata), _ptr(nchara, C.c_ubyte),
+                                     _ptr(charamap, C.c_ubyte)))
+        self.n, self.ns, self.npatt = n, ns, npatt
+
+    def set_tree(self, root, nson, sons, scale_flags=None):
+        nson = np.ascontiguousarray(nson, np.int32)
+        sons = np.ascontiguousarray(sons, np.int32)
+        flags = None if scale_flags is None else np.ascontiguousarray(scale_flags, np.uint8)
+        nnode = nson.shape[0]
+        check(self._L.pb200_set_tree(self._ctx, C.c_int(nnode), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
+                                     C.c_int(sons.shape[1]), _ptr(flags, C.c_ubyte)))
+        self.nnode = nnode
+
+    def set_problem(self, p, h0=0, h1=None):
+        """Upload the static part of a Problem, optionally only the pattern shard [h0, h1)."""
+        h1 = p.npatt if h1 is None else h1
+        self.set_data(p.n, p.z[:, h0:h1], p.fpatt[h0:h1], p.cleandata, p.nchara, p.charamap)
+        self.set_tree(p.root, p.nson, p.sons, p.scale_flags)
+
+    # -- per evaluation ---------------------------------------------------------------------------
+    def eval(self, semantics, freqK, set_kind, nr, set_data, branch_set, branch_t, pi):
+        freqK = np.ascontiguousarray(freqK, np.float64)
+        set_data = np.ascontiguousarray(set_data, np.float64)
+        if set_data.ndim == 1:
+            set_data = set_data.reshape(1, -1)
+        branch_set = np.ascontiguousarray(branch_set, np.int32)
+        branch_t = np.ascontiguousarray(branch_t, np.float64)
+        pi = np.ascontiguousarray(pi, np.float64)
+        nclass = freqK.shape[0]
+        assert branch_set.shape == (nclass, self.nnode) and branch_t.shape == (nclass, self.nnode)
+        out = C.c_double(0)
+        check(self._L.pb200_eval(self._ctx, C.c_int(semantics), C.c_int(nclass), _ptr(freqK, C.c_double),
+                                 C.c_int(set_kind), C.c_int(nr), C.c_int(set_data.shape[0]),
+                                 C.c_longlong(set_data.shape[1]), _ptr(set_data, C.c_double),
+                                 _ptr(branch_set, C.c_int), _ptr(branch_t, C.c_double), _ptr(pi, C.c_double),
+                                 C.byref(out)))
+        self.nclass = nclass
+        return out.value
+
+    def eval_problem(self, p):
+        return self.eval(p.semantics, p.freqK, p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, p.pi)
+
+    def lnf(self):
+        out = np.zeros(self.npatt)
+        check(self._L.pb200_get_lnf(self._ctx, _ptr(out, C.c_double)))
+        return out
+
+    def fhK(self):
+        out = np.zeros((self.nclass, self.npatt))
+        check(self._L.pb200_get_fhK(self._ctx, _ptr(out, C.c_double)))
+        return out
+
+    def pmat(self, n, set_kind, nr, set_data, mat_set, mat_t):
+        set_data = np.ascontiguousarray(set_data, np.float64)
+        if set_data.ndim == 1:
+            set_data = set_data.reshape(1, -1)
+        mat_set = np.ascontiguousarray(mat_set, np.int32)
+        mat_t = np.ascontiguousarray(mat_t, np.float64)
+        nmat = mat_set.shape[0]
+        out = np.zeros((nmat, n, n))
+        check(self._L.pb200_pmat(self._ctx, C.c_int(n), C.c_int(set_kind), C.c_int(nr), C.c_int(set_data.shape[0]),
+                                 C.c_longlong(set_data.shape[1]), _ptr(set_data, C.c_double), C.c_int(nmat),
+                                 _ptr(mat_set, C.c_int), _ptr(mat_t, C.c_double), _ptr(out, C.c_double)))
+        return out
+
+    # -- multi-GPU --------------------------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        check(lib().pb200_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid):
+        check(self._L.pb200_comm_init(self._ctx, C.c_int(nranks), C.c_int(rank), C.c_char_p(uid)))
+
+    # -- timing / introspection -------------------------------------------------------------------
+    def set_timing(self, enable=True):
+        check(self._L.pb200_set_timing(self._ctx, C.c_int(1 if enable else 0)))
+
+    def last_timing(self):
+        ms = (C.c_double * 5)()
+        check(self._L.pb200_last_timing(self._ctx, ms))
+        return dict(total=ms[0], pt=ms[1], prune=ms[2], mix=ms[3], allreduce=ms[4])
+
+    def launch_count(self):
+        return int(self._L.pb200_launch_count(self._ctx))
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(0), C.c_double(0)
+        check(self._L.pb200_measure_fp64_peak(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def flush_l2(self, nbytes=256 << 20):
+        check(self._L.pb200_flush_l2(self._ctx, C.c_longlong(nbytes)))

@@ -1,0 +1,73 @@
+"""Host logic without a GPU: the planner's program interpreted in numpy must reproduce the oracle."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_ids
+from paml_b200.fixture import load_fixture
+from paml_b200 import likelihood, simulate
+from oracle import oracle
+from simprog import run_program
+
+
+def _pmat_fn(p):
+    cache = {}
+    def f(cls, node):
+        key = (cls, node)
+        if key not in cache:
+            cache[key] = oracle.pmat(p.branch_t[cls, node], p.n, p.set_kind, p.nr, p.set_data[p.branch_set[cls, node]])
+        return cache[key]
+    return f
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=golden_ids())
+def test_program_reproduces_reference(path):
+    p = load_fixture(path)
+    prog, nslots = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags)
+    v, lnf = run_program(prog, nslots, p, _pmat_fn(p))
+    assert abs(v - p.ref_neg_lnL) <= 1e-10 * abs(p.ref_neg_lnL)
+    np.testing.assert_allclose(lnf, p.ref_lnf, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape,ns", [("random", 40), ("balanced", 64), ("caterpillar", 30), ("random", 5)])
+def test_program_on_synthetic_trees(shape, ns):
+    from paml_b200.tree import random_tree
+    p = simulate.nuc_gtr_gamma_problem(ns=ns, npatt=300, seed=11 + ns, K=3)
+    t = random_tree(ns, 5 + ns, shape=shape)
+    p.father, p.nson, p.sons, p.root, p.nnode, p.maxsons = t.father, t.nson, t.sons, t.root, t.nnode, t.maxsons
+    p.branch_t = np.array([1.0, 0.3, 2.0])[:, None] * t.branch[None, :]
+    p.branch_set = np.zeros((3, t.nnode), np.int32)
+    p.nscale, p.scale_flags = likelihood.default_scale_flags(t.nnode, t.root, t.nson, t.sons, 7)
+    prog, nslots = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags)
+    # slot need is logarithmic for balanced trees and 1-2 for caterpillars
+    assert nslots <= int(np.ceil(np.log2(ns))) + 1
+    if shape == "caterpillar":
+        assert nslots <= 2
+    r = oracle.lnl(p)
+    v, lnf = run_program(prog, nslots, p, _pmat_fn(p))
+    assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
+
+
+def test_multifurcation_is_folded():
+    # star-like root with 5 internal children must not need 5 slots
+    from paml_b200.tree import parse_newick
+    t = parse_newick("((1:.1,2:.1):.1,(3:.1,4:.1):.1,(5:.1,6:.1):.1,(7:.1,8:.1):.1,(9:.1,10:.1):.1,11:.2);")
+    prog, nslots = likelihood.plan_tree(t.nnode, t.ns, t.root, t.nson, t.sons, None)
+    assert nslots == 2
+
+
+def test_plan_rejects_bad_trees():
+    nson = np.array([0, 0, 2], np.int32)
+    sons = np.array([[-1, -1], [-1, -1], [0, 0]], np.int32)
+    with pytest.raises(likelihood.PB200Error):
+        likelihood.plan_tree(3, 2, 2, nson, sons, None)
+    with pytest.raises(likelihood.PB200Error):
+        likelihood.plan_tree(3, 2, 0, nson, sons, None)      # root must be internal
+
+
+def test_default_scale_flags_match_reference():
+    for g in GOLDEN:
+        p = load_fixture(g)
+        every = {0: 100, 1: 15, 2: 50}[p.seqtype]
+        k, flags = likelihood.default_scale_flags(p.nnode, p.root, p.nson, p.sons, every)
+        assert k == p.nscale
+        np.testing.assert_array_equal(flags, p.scale_flags)
