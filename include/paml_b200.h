@@ -114,6 +114,12 @@ int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *son
 /* FP64 peak micro-benchmark on the context's GPU: tensor (DMMA m8n8k4) and vector (DFMA) TFLOP/s.
  * MEASURED_PEAKS.json has no FP64 figure; bench.py uses this as the FP64 roofline denominator.          */
 int pb200_measure_fp64_peak(pb200_ctx *ctx, double *dmma_tflops, double *dfma_tflops);
+/* Device-resident throughput: re-run the kernels of the last pb200_eval (parameters, data and tree already in
+ * HBM) `steps` times back to back on the context's stream, optionally writing flush_bytes of scratch before
+ * each step to evict L2, and report per-step device times (ms, CUDA events on that stream): whole step,
+ * P(t) kernel, pruning kernel, mixture kernel (+ all-reduce when a communicator is set).                   */
+int pb200_bench_resident(pb200_ctx *ctx, int steps, long long flush_bytes, double *ms_step, double *ms_pt,
+                         double *ms_prune, double *ms_mix);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 int pb200_flush_l2(pb200_ctx *ctx, long long bytes);
 

@@ -113,6 +113,8 @@ struct pb200_ctx {
     double* h_result = nullptr;
     int last_nclass = 0;
     bool have_eval = false;
+    // parameters of the last evaluation, resident in d_stage (for pb200_bench_resident)
+    struct { int semantics, nclass, kind, nr, nmat, mix_blocks; long long set_stride; size_t off_freq, off_pi, off_sets, off_t, off_set; } last = {};
     // comm
     nccl_comm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -403,6 +405,35 @@ static int check_sets(int n, int set_kind, int nr, int nset, long long set_strid
     return 0;
 }
 
+// The device side of one evaluation: P(t) for all (class, branch) -> pruning -> mixture/sum [-> all-reduce].
+// ev (optional): 4 events recorded before P(t), before pruning, before the mixture, after everything.
+static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
+{
+    char* ds = (char*)c->d_stage.p;
+    const auto& L = c->last;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[0], c->stream));
+    if (launch_pt(c, c->n, L.kind, L.nr, L.set_stride, (const double*)(ds + L.off_sets), L.nmat, (const int*)(ds + L.off_set),
+                  (const double*)(ds + L.off_t), (double*)c->d_P.p, c->pstride, PT_MODE_AUTO, c->nnode, c->ns, c->NT, c->KS, c->ncodes))
+        return 1;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[1], c->stream));
+    if (launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2], c->stream));
+    {
+        MixParams mp;
+        mp.fhK = (const double*)c->d_fhK.p; mp.fpatt = (const double*)c->d_fpatt.p; mp.freqK = (const double*)(ds + L.off_freq);
+        mp.lnf = (double*)c->d_lnf.p; mp.partial = (double*)c->d_partial.p; mp.counter = (unsigned int*)c->d_counter.p;
+        mp.result = (double*)c->d_result.p; mp.npatt = c->npatt; mp.nclass = L.nclass; mp.semantics = L.semantics;
+        mp.nscale = c->plan.nscale;
+        mix_kernel<<<L.mix_blocks, 256, 0, c->stream>>>(mp);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (c->comm && c->nranks > 1)
+        NCCL_TRY(g_nccl.AllReduce(c->d_result.p, c->d_result.p, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[3], c->stream));
+    return 0;
+}
+
 extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double* freqK, int set_kind, int nr, int nset,
                           long long set_stride, const double* set_data, const int* branch_set, const double* branch_t,
                           const double* pi, double* neg_lnL)
@@ -448,28 +479,15 @@ extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double*
     if (c->d_partial.ensure((size_t)mix_blocks * 8)) return 1;
 
     char* ds = (char*)c->d_stage.p;
+    c->last.semantics = semantics; c->last.nclass = nclass; c->last.kind = set_kind; c->last.nr = nr; c->last.nmat = nmat;
+    c->last.mix_blocks = mix_blocks; c->last.set_stride = set_stride;
+    c->last.off_freq = off_freq; c->last.off_pi = off_pi; c->last.off_sets = off_sets; c->last.off_t = off_t; c->last.off_set = off_set;
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     CUDA_TRY(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, c->stream));
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
-                  (const double*)(ds + off_t), (double*)c->d_P.p, c->pstride, PT_MODE_AUTO, nnode, c->ns, c->NT, c->KS, c->ncodes))
-        return 1;
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    if (launch_prune(c, nclass, semantics, (const double*)(ds + off_pi))) return 1;
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     {
-        MixParams mp;
-        mp.fhK = (const double*)c->d_fhK.p; mp.fpatt = (const double*)c->d_fpatt.p; mp.freqK = (const double*)(ds + off_freq);
-        mp.lnf = (double*)c->d_lnf.p; mp.partial = (double*)c->d_partial.p; mp.counter = (unsigned int*)c->d_counter.p;
-        mp.result = (double*)c->d_result.p; mp.npatt = c->npatt; mp.nclass = nclass; mp.semantics = semantics;
-        mp.nscale = c->plan.nscale;
-        mix_kernel<<<mix_blocks, 256, 0, c->stream>>>(mp);
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
+        cudaEvent_t evs[4] = {c->ev[1], c->ev[2], c->ev[3], c->ev[4]};
+        if (run_kernels(c, c->timing ? evs : nullptr)) return 1;
     }
-    if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    if (c->comm && c->nranks > 1)
-        NCCL_TRY(g_nccl.AllReduce(c->d_result.p, c->d_result.p, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -478,11 +496,11 @@ extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double*
     c->have_eval = true;
     if (c->timing) {
         float ms;
-        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); c->last_ms[0] = ms;
-        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;
-        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[2] = ms;
-        cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->last_ms[3] = ms;
-        cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->last_ms[4] = ms;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); c->last_ms[0] = ms;   // H2D + kernels (+ all-reduce)
+        cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->last_ms[1] = ms;   // P(t)
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->last_ms[2] = ms;   // pruning
+        cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->last_ms[3] = ms;   // mixture + sum (+ all-reduce)
+        c->last_ms[4] = 0;
     }
     return 0;
 }
@@ -605,6 +623,38 @@ extern "C" int pb200_measure_fp64_peak(pb200_ctx* c, double* dmma_tflops, double
     if (dmma_tflops) *dmma_tflops = best[0];
     if (dfma_tflops) *dfma_tflops = best[1];
     return 0;
+}
+
+extern "C" int pb200_bench_resident(pb200_ctx* c, int steps, long long flush_bytes, double* ms_step, double* ms_pt,
+                                    double* ms_prune, double* ms_mix)
+{
+    if (!c) return fail("pb200_bench_resident: null context");
+    if (!c->have_eval) return fail("pb200_bench_resident: call pb200_eval once first (it makes the parameters resident)");
+    if (steps < 1 || steps > 4096) return fail("pb200_bench_resident: bad steps");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<cudaEvent_t> ev((size_t)steps * 4);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    int rc = 0;
+    for (int i = 0; i < steps && !rc; i++) {
+        if (flush_bytes > 0) rc = pb200_flush_l2(c, flush_bytes);
+        if (!rc) rc = run_kernels(c, &ev[(size_t)i * 4]);
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (!rc && e != cudaSuccess) rc = fail("pb200_bench_resident: %s", cudaGetErrorString(e));
+    if (!rc)
+        for (int i = 0; i < steps; i++) {
+            float a, b, d, t;
+            cudaEventElapsedTime(&t, ev[i * 4 + 0], ev[i * 4 + 3]);
+            cudaEventElapsedTime(&a, ev[i * 4 + 0], ev[i * 4 + 1]);
+            cudaEventElapsedTime(&b, ev[i * 4 + 1], ev[i * 4 + 2]);
+            cudaEventElapsedTime(&d, ev[i * 4 + 2], ev[i * 4 + 3]);
+            if (ms_step) ms_step[i] = t;
+            if (ms_pt) ms_pt[i] = a;
+            if (ms_prune) ms_prune[i] = b;
+            if (ms_mix) ms_mix[i] = d;
+        }
+    for (auto& x : ev) cudaEventDestroy(x);
+    return rc;
 }
 
 extern "C" int pb200_flush_l2(pb200_ctx* c, long long bytes)

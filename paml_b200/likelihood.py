@@ -165,5 +165,12 @@ class TreeLikelihood:
         check(self._L.pb200_measure_fp64_peak(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def bench_resident(self, steps, flush_bytes=0):
+        """Per-step device times (ms) of `steps` back-to-back evaluations with everything resident in HBM."""
+        arrs = [np.zeros(steps) for _ in range(4)]
+        check(self._L.pb200_bench_resident(self._ctx, C.c_int(steps), C.c_longlong(flush_bytes),
+                                           *[_ptr(a, C.c_double) for a in arrs]))
+        return dict(step=arrs[0], pt=arrs[1], prune=arrs[2], mix=arrs[3])
+
     def flush_l2(self, nbytes=256 << 20):
         check(self._L.pb200_flush_l2(self._ctx, C.c_longlong(nbytes)))
