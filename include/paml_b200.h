@@ -114,6 +114,10 @@ int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *son
 /* FP64 peak micro-benchmark on the context's GPU: tensor (DMMA m8n8k4) and vector (DFMA) TFLOP/s.
  * MEASURED_PEAKS.json has no FP64 figure; bench.py uses this as the FP64 roofline denominator.          */
 int pb200_measure_fp64_peak(pb200_ctx *ctx, double *dmma_tflops, double *dfma_tflops);
+/* Kernel-tuning aid: replace the pruning program of the current tree by a hand-made one (same format as
+ * pb200_plan_tree writes), e.g. only tip children or only internal children, to time the phases of the
+ * pruning kernel in isolation.  Results of evaluations after this call are meaningless.                    */
+int pb200_debug_set_program(pb200_ctx *ctx, const int *prog, int nints, int nslots, int nscale);
 /* Device-resident throughput: re-run the kernels of the last pb200_eval (parameters, data and tree already in
  * HBM) `steps` times back to back on the context's stream, optionally writing flush_bytes of scratch before
  * each step to evict L2, and report per-step device times (ms, CUDA events on that stream): whole step,

@@ -232,7 +232,7 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
     c->n = n; c->ns = ns; c->npatt = npatt; c->zstride = zstride; c->cleandata = cleandata; c->ncodes = ncodes;
     choose_shape(n, &c->NT, &c->KS);
     c->ld = 4 * c->KS;
-    c->pstride = std::max<long long>((long long)c->KS * c->NT * 32, (long long)ncodes * 8 * c->NT);
+    c->pstride = std::max<long long>((long long)c->KS * ((c->NT + 1) / 2) * 64, (long long)ncodes * 8 * c->NT);
     c->have_eval = false;
     return 0;
 }
@@ -294,10 +294,12 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
     return 0;
 }
 
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
 // ---- pruning kernel dispatch ----
 struct PruneLaunch {
     void (*fn)(const PruneParams);
-    int rows, slot_doubles, max_warps;
+    int rows, slot_doubles, max_warps, ring_bytes;
 };
 template <int NT, int KS, int MT, int MAXW>
 static PruneLaunch make_launch()
@@ -307,11 +309,12 @@ static PruneLaunch make_launch()
     L.rows = PruneCfg<NT, KS, MT>::ROWS;
     L.slot_doubles = PruneCfg<NT, KS, MT>::SLOT_DOUBLES;
     L.max_warps = MAXW;
+    L.ring_bytes = PruneCfg<NT, KS, MT>::RING_BYTES;
     return L;
 }
 static int pick_launch(int NT, int mt_small, PruneLaunch* L)
 {
-    if (NT == 8) *L = mt_small ? make_launch<8, 16, 1, 8>() : make_launch<8, 16, 2, 8>();
+    if (NT == 8) *L = mt_small ? make_launch<8, 16, 1, 16>() : make_launch<8, 16, 2, 8>();
     else if (NT == 3) *L = mt_small ? make_launch<3, 5, 1, 16>() : make_launch<3, 5, 2, 16>();
     else if (NT == 1) *L = mt_small ? make_launch<1, 1, 1, 16>() : make_launch<1, 1, 4, 16>();
     else return fail("no pruning kernel for NT = %d", NT);
@@ -332,9 +335,10 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     PruneLaunch L;
     int warps = 0;
     size_t per_warp = 0;
-    for (int small = 0; small < 2 && warps == 0; small++) {
+    const char* mtenv = getenv("PB200_MT_SMALL");
+    for (int small = (mtenv && atoi(mtenv)) ? 1 : 0; small < 2 && warps == 0; small++) {
         if (pick_launch(c->NT, small, &L)) return 1;
-        per_warp = (size_t)c->plan.nslots * L.slot_doubles * sizeof(double);
+        per_warp = align16((size_t)c->plan.nslots * L.slot_doubles * sizeof(double) + L.ring_bytes);
         size_t budget = smem_budget();
         warps = (int)std::min<size_t>(L.max_warps, budget / per_warp);
         if (warps == 0 && small == 1) warps = (int)std::min<size_t>(L.max_warps, (size_t)227 * 1024 / per_warp);
@@ -348,17 +352,30 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     p.prog = (const int*)c->d_prog.p;
     p.z = (const unsigned char*)c->d_z.p;
     p.zstride = c->zstride; p.npatt = c->npatt;
-    p.ntiles = (c->npatt + L.rows - 1) / L.rows;
-    p.nitems = p.ntiles * nclass;
     p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
     p.nnode = c->nnode; p.nclass = nclass; p.nslots = c->plan.nslots; p.n = c->n;
     p.semantics = semantics; p.nscale = c->plan.nscale;
     p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
+    p.tile_counter = (unsigned int*)c->d_counter.p + 4;
+    p.warp_smem_bytes = (int)per_warp;
+    {
+        // one "pipe phase" = the DMMA time of one item when a warp has the pipe to itself:
+        // (internal children per walk) x (DMMAs per child) x 16 cycles per DMMA, at ~1.9 GHz
+        const char* senv = getenv("PB200_STAGGER_NS");
+        double dmma_per_child = (double)c->KS * c->NT * (L.rows / 8);
+        double cycles = (double)c->plan.n_internal_children * dmma_per_child * 16.0;
+        p.stagger_ns = senv ? (unsigned int)atol(senv) : (unsigned int)std::min(2.0e6, cycles / 1.9);
+        if (warps <= 4) p.stagger_ns = 0;
+    }
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, L.fn, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    p.ntiles = (c->npatt + L.rows - 1) / L.rows;
+    p.nitems = p.ntiles * nclass;
     long long want = (p.nitems + warps - 1) / warps;
     int grid = (int)std::min<long long>(want, (long long)c->nsm * per_sm);
+    const char* genv = getenv("PB200_GRID");
+    if (genv && atoi(genv) > 0) grid = atoi(genv);
     if (grid < 1) grid = 1;
     L.fn<<<grid, warps * 32, smem, c->stream>>>(p);
     c->launches++;
@@ -382,7 +399,6 @@ static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride
     return 0;
 }
 
-static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 static int check_sets(int n, int set_kind, int nr, int nset, long long set_stride)
 {
@@ -422,6 +438,7 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         MixParams mp;
         mp.fhK = (const double*)c->d_fhK.p; mp.fpatt = (const double*)c->d_fpatt.p; mp.freqK = (const double*)(ds + L.off_freq);
         mp.lnf = (double*)c->d_lnf.p; mp.partial = (double*)c->d_partial.p; mp.counter = (unsigned int*)c->d_counter.p;
+        mp.tile_counter = (unsigned int*)c->d_counter.p + 4;
         mp.result = (double*)c->d_result.p; mp.npatt = c->npatt; mp.nclass = L.nclass; mp.semantics = L.semantics;
         mp.nscale = c->plan.nscale;
         mix_kernel<<<L.mix_blocks, 256, 0, c->stream>>>(mp);
@@ -622,6 +639,19 @@ extern "C" int pb200_measure_fp64_peak(pb200_ctx* c, double* dmma_tflops, double
     out.release();
     if (dmma_tflops) *dmma_tflops = best[0];
     if (dfma_tflops) *dfma_tflops = best[1];
+    return 0;
+}
+
+extern "C" int pb200_debug_set_program(pb200_ctx* c, const int* prog, int nints, int nslots, int nscale)
+{
+    if (!c || !prog || nints < PROG_HDR) return fail("pb200_debug_set_program: bad arguments");
+    if (c->nnode == 0) return fail("pb200_debug_set_program: call pb200_set_tree first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->d_prog.ensure((size_t)nints * sizeof(int))) return 1;
+    CUDA_TRY(cudaMemcpyAsync(c->d_prog.p, prog, (size_t)nints * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->plan.prog.assign(prog, prog + nints);
+    c->plan.nops = prog[0]; c->plan.nslots = nslots; c->plan.nscale = nscale;
     return 0;
 }
 

@@ -167,12 +167,15 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
         }
     }
     else {
-        // DMMA B-fragment order: element (ks, nt, lane) = P[8nt + lane/4][4ks + lane%4]
-        const int total = p.KS * p.NT * 32;
-        for (int e = tid; e < total; e += 256) {
-            int lane = e & 31, f = e >> 5, nt = f % p.NT, ks = f / p.NT;
+        // DMMA B-fragment order, two n-tiles per 16-byte element so that one LDG.128 feeds two DMMAs:
+        // element (ks, pr, lane, e) = P[8*(2pr+e) + lane/4][4ks + lane%4]
+        const int NTP = (p.NT + 1) / 2;
+        const int total = p.KS * NTP * 64;
+        for (int e0 = tid; e0 < total; e0 += 256) {
+            int e = e0 & 1, lane = (e0 >> 1) & 31, f = e0 >> 6, pr = f % NTP, ks = f / NTP;
+            int nt = 2 * pr + e;
             int j = 8 * nt + (lane >> 2), k = 4 * ks + (lane & 3);
-            out[e] = (j < n && k < n) ? Psm[j * ld + k] : 0.0;
+            out[e0] = (nt < p.NT && j < n && k < n) ? Psm[j * ld + k] : 0.0;
         }
     }
 }
@@ -189,6 +192,9 @@ struct PruneParams {
     int nnode, nclass, nslots, n, semantics, nscale;
     const double* pi;           // [8*NT] zero padded
     double* fhK;                // [nclass][npatt]
+    unsigned int* tile_counter; // dynamic work distribution (reset by mix_kernel)
+    int warp_smem_bytes;        // shared memory per warp: slots + tip-code ring
+    unsigned int stagger_ns;    // start delay between the warps that share an SM sub-partition (see kernel)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
@@ -196,60 +202,169 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+// tip gathers stream through: read-only path, no L1 allocation (L1 is kept for the B fragments)
+__device__ __forceinline__ double2 ld_gather(const double2* ptr)
+{
+#ifdef PB200_GATHER_L1
+    return __ldg(ptr);
+#else
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+    return v;
+#endif
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
 template <int NT, int KS, int MT>
 struct PruneCfg {
     static constexpr int NP = 8 * NT;                       // padded output states
     static constexpr int KP = 4 * KS;                       // padded input states
-    // row stride of a slot: conflict-free A-fragment loads need stride % 16 in {4, 12}
-    static constexpr int STRIDE = (KP % 16 == 4 || KP % 16 == 12) ? KP : KP + 4;
+    static constexpr int NTP = (NT + 1) / 2;                // n-tile pairs in a B-fragment element
+    // Slot rows: stride % 16 == 8 doubles plus an XOR-4 column swizzle on rows with bit 1 of (row % 8) set
+    // makes BOTH the 8-byte A-fragment loads and the 16-byte C-fragment stores bank-conflict free.
+    static constexpr int STRIDE = ((KP + 7) / 16) * 16 + 8;
     static constexpr int ROWS = 8 * MT;                     // patterns per warp
     static constexpr int SLOT_DOUBLES = ROWS * STRIDE;
+    static constexpr int RING = 8;                          // tips whose codes are prefetched ahead
+    static constexpr int RING_BYTES = RING * ROWS;
+    static_assert(STRIDE >= KP + 4 || KP % 8 == 0, "swizzled columns must stay inside the row");
 };
 
 // One warp owns ROWS site patterns of one site class and walks the whole tree for them; conditional
 // vectors stay in registers (the node being built, C-fragment layout) and in the warp's private shared
 // memory slots (finished children, [pattern][state] rows).  No block-level synchronisation at all.
+// Tip codes are streamed through a small per-warp cp.async ring a few tips ahead of their use, so the
+// HBM latency of the alignment never sits on the critical path.
 template <int NT, int KS, int MT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams p)
 {
     using C = PruneCfg<NT, KS, MT>;
-    extern __shared__ __align__(16) double sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;   // nw <= WARPS
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    double* slots = sm + (size_t)warp * p.nslots * C::SLOT_DOUBLES;
+    const int xsw = ((g >> 1) & 1) * 4;                     // column swizzle of this lane's rows
+    double* slots = reinterpret_cast<double*>(smraw + (size_t)warp * p.warp_smem_bytes);
+    unsigned char* ring = reinterpret_cast<unsigned char*>(slots + (size_t)p.nslots * C::SLOT_DOUBLES);
     const long long N = p.npatt;
+    const int nops = p.prog[0], ntip = p.prog[2];
+    const int* tip_order = p.prog + PROG_HDR;
+    const int* ops = p.prog + p.prog[3];
 
-    for (long long item = (long long)blockIdx.x * nw + warp; item < p.nitems; item += (long long)gridDim.x * nw) {
+    // Warps that share a sub-partition (same warp % 4) share one DMMA pipe.  Started together they stay in
+    // lockstep -- all gathering tips at once, then all queueing on the tensor pipe -- and the phases simply add
+    // up.  Starting them one pipe-phase apart lets one warp's tip gathers/stores run under another's DMMAs.
+    if (p.stagger_ns) {
+        unsigned long long wait_ns = (unsigned long long)(warp >> 2) * p.stagger_ns;
+        while (wait_ns > 0) { unsigned int chunk = wait_ns > 500000ull ? 500000u : (unsigned int)wait_ns; __nanosleep(chunk); wait_ns -= chunk; }
+    }
+
+    for (;;) {
+        unsigned int item_u = 0;
+        if (lane == 0) item_u = atomicAdd(p.tile_counter, 1u);
+        const long long item = __shfl_sync(0xffffffffu, item_u, 0);
+        if (item >= p.nitems) break;
         const int cls = (int)(item / p.ntiles);
         const long long h0 = (item - (long long)cls * p.ntiles) * C::ROWS;
         const double* Pcls = p.Pbuf + (size_t)cls * p.nnode * p.pstride;
+        const unsigned char* zt = p.z + h0;
         double lnsc[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) lnsc[mt] = 0.0;
 
-        const int* pc = p.prog + 2;
-        const int nops = p.prog[0];
+        // prologue of the tip-code ring: the first RING tips of the walk
+#pragma unroll
+        for (int i = 0; i < C::RING; i++) {
+            if (i < ntip && lane < C::ROWS / 4) cp_async4(ring + i * C::ROWS + 4 * lane, zt + (size_t)tip_order[i] * p.zstride + 4 * lane);
+            cp_async_commit();
+        }
+        int ti = 0;                                          // tips consumed so far
+
+        const int* pc = ops;
         for (int op = 0; op < nops; op++) {
-            const int nchild = pc[0], out_slot = pc[1], sidx = pc[2];
+            const int nchild = pc[0], out_slot = pc[1], sidx = pc[2], ntip_op = pc[5];
             pc += OP_HDR;
             double acc[MT][NT][2];
+            double tmp[MT][NT][2];
+            int c = 0;
+            if (ntip_op > 0) {
+                // Tips first (src/codeml.c:3555-3567): acc[h][j] = PT_a[z_a,h][j] (* PT_b[z_b,h][j]).  The gathers of
+                // up to two tips are issued back to back straight into acc / tmp, so their L2 latency overlaps
+                // and, for a node that also has internal children, hides behind the DMMA work that follows.
+                const bool two = (ntip_op > 1);
+                cp_async_wait<C::RING - 2>();
+                __syncwarp();
+                const unsigned char* zr0 = ring + (ti % C::RING) * C::ROWS;
+                const unsigned char* zr1 = ring + ((ti + 1) % C::RING) * C::ROWS;
+                int code0[MT], code1[MT];
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++)
+                for (int mt = 0; mt < MT; mt++) { code0[mt] = zr0[8 * mt + g]; code1[mt] = two ? zr1[8 * mt + g] : 0; }
+                __syncwarp();
+                for (int k = 0; k < (two ? 2 : 1); k++) {   // refill the ring entries just consumed
+                    const int nx = ti + k + C::RING;
+                    if (nx < ntip && lane < C::ROWS / 4)
+                        cp_async4(ring + ((ti + k) % C::RING) * C::ROWS + 4 * lane, zt + (size_t)tip_order[nx] * p.zstride + 4 * lane);
+                    cp_async_commit();
+                }
+                ti += two ? 2 : 1;
+                const double* Pm0 = Pcls + (size_t)pc[2] * p.pstride;
+                const double* Pm1 = Pcls + (size_t)pc[two ? CH_REC + 2 : 2] * p.pstride;
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 1.0;
+                for (int mt = 0; mt < MT; mt++) {
+                    const double2* row = reinterpret_cast<const double2*>(Pm0 + (size_t)code0[mt] * C::NP);
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) { double2 v = ld_gather(row + nt * 4 + q); acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y; }
+                }
+                if (two) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double2* row = reinterpret_cast<const double2*>(Pm1 + (size_t)code1[mt] * C::NP);
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) { double2 v = ld_gather(row + nt * 4 + q); tmp[mt][nt][0] = v.x; tmp[mt][nt][1] = v.y; }
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] *= tmp[mt][nt][0]; acc[mt][nt][1] *= tmp[mt][nt][1]; }
+                }
+                c = two ? 2 : 1;
+                pc += c * CH_REC;
+            }
+            else {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 1.0;
+            }
 
-            for (int c = 0; c < nchild; c++) {
+            for (; c < nchild; c++) {
                 const int kind = pc[0], idx = pc[1], node = pc[2];
                 pc += CH_REC;
                 const double* Pm = Pcls + (size_t)node * p.pstride;
                 if (kind == CH_TIP) {
-                    // acc[h][j] *= PT[z_h][j]                          (src/codeml.c:3555-3567)
+                    // third and later tips of a multifurcation: one at a time
+                    cp_async_wait<C::RING - 1>();
+                    __syncwarp();
+                    const unsigned char* zr = ring + (ti % C::RING) * C::ROWS;
+                    int code[MT];
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) code[mt] = zr[8 * mt + g];
+                    __syncwarp();
+                    {
+                        const int nx = ti + C::RING;
+                        if (nx < ntip && lane < C::ROWS / 4)
+                            cp_async4(ring + (ti % C::RING) * C::ROWS + 4 * lane, zt + (size_t)tip_order[nx] * p.zstride + 4 * lane);
+                        cp_async_commit();
+                    }
+                    ti++;
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
-                        long long h = h0 + 8 * mt + g;
-                        int code = (h < N) ? (int)p.z[(size_t)idx * p.zstride + h] : 0;
-                        const double2* row = reinterpret_cast<const double2*>(Pm + (size_t)code * C::NP);
+                        const double2* row = reinterpret_cast<const double2*>(Pm + (size_t)code[mt] * C::NP);
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
                             double2 v = __ldg(row + nt * 4 + q);
@@ -260,18 +375,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 else if (kind == CH_INTERNAL) {
                     // acc[h][j] *= sum_k P[j][k] L_child[h][k]           (src/codeml.c:3568-3575) on DMMA
                     const double* S = slots + (size_t)idx * C::SLOT_DOUBLES;
-                    double tmp[MT][NT][2];
+                    const double2* B = reinterpret_cast<const double2*>(Pm) + lane;
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) tmp[mt][nt][0] = tmp[mt][nt][1] = 0.0;
 #pragma unroll
                     for (int ks = 0; ks < KS; ks++) {
-                        double a[MT], b[NT];
+                        double a[MT], b[2 * C::NTP];
 #pragma unroll
-                        for (int mt = 0; mt < MT; mt++) a[mt] = S[(8 * mt + g) * C::STRIDE + 4 * ks + q];
+                        for (int mt = 0; mt < MT; mt++) a[mt] = S[(8 * mt + g) * C::STRIDE + ((4 * ks + q) ^ xsw)];
 #pragma unroll
-                        for (int nt = 0; nt < NT; nt++) b[nt] = __ldg(Pm + (ks * NT + nt) * 32 + lane);
+                        for (int pr = 0; pr < C::NTP; pr++) {
+                            double2 v = __ldg(B + (ks * C::NTP + pr) * 32);
+                            b[2 * pr] = v.x; b[2 * pr + 1] = v.y;
+                        }
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++)
 #pragma unroll
@@ -290,7 +408,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
                             if (8 * nt + 2 * q < C::KP) {
-                                double2 v = *reinterpret_cast<const double2*>(S + (8 * mt + g) * C::STRIDE + 8 * nt + 2 * q);
+                                double2 v = *reinterpret_cast<const double2*>(S + (8 * mt + g) * C::STRIDE + ((8 * nt + 2 * q) ^ xsw));
                                 acc[mt][nt][0] *= v.x; acc[mt][nt][1] *= v.y;
                             }
                         }
@@ -329,7 +447,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++)
                         if (8 * nt + 2 * q < C::KP)
-                            *reinterpret_cast<double2*>(S + (8 * mt + g) * C::STRIDE + 8 * nt + 2 * q) =
+                            *reinterpret_cast<double2*>(S + (8 * mt + g) * C::STRIDE + ((8 * nt + 2 * q) ^ xsw)) =
                                 make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                 __syncwarp();
             }
@@ -363,6 +481,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 }
             }
         }
+        cp_async_wait<0>();
         __syncwarp();
     }
 }
@@ -377,6 +496,7 @@ struct MixParams {
     double* lnf;            // [npatt] out
     double* partial;        // [gridDim.x] scratch
     unsigned int* counter;  // zero-initialised, reset by the last block
+    unsigned int* tile_counter;  // pruning kernel's work counter: reset here for the next evaluation
     double* result;         // [1] out: -lnL of this shard
     long long npatt;
     int nclass, semantics, nscale;
@@ -430,7 +550,7 @@ __global__ void __launch_bounds__(256) mix_kernel(const MixParams p)
         red[tid] = t;
         __syncthreads();
         for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
-        if (tid == 0) { p.result[0] = red[0]; *p.counter = 0u; }
+        if (tid == 0) { p.result[0] = red[0]; *p.counter = 0u; *p.tile_counter = 0u; }
     }
 }
 

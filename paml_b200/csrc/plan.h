@@ -6,13 +6,15 @@
 
 namespace pb200 {
 
-// op header: {nchild, out_slot, scale_idx, node, flags}; child record: {kind, idx, node}
-enum { OP_HDR = 5, CH_REC = 3 };
+// program: [nops, nslots, ntip, first_op_offset] [tip rows in the order the walk consumes them] ops...
+// op header: {nchild, out_slot, scale_idx, node, flags, ntip}; child record: {kind, idx, node};
+// the ntip tip children of an op come first in its child list.
+enum { PROG_HDR = 4, OP_HDR = 6, CH_REC = 3 };
 enum { CH_TIP = 0, CH_INTERNAL = 1, CH_PARTIAL = 2 };
 enum { OPF_PARTIAL_OUT = 1 };
 
 struct Plan {
-    std::vector<int> prog;      // prog[0] = nops, prog[1] = nslots, then ops
+    std::vector<int> prog;      // see layout above
     int nops = 0, nslots = 0, nscale = 0;
     long long n_internal_children = 0, n_tip_children = 0;   // per tree walk (for flop / byte accounting)
 };

@@ -3,7 +3,7 @@ planner (op order, slot reuse, folded multifurcations, scale indices) without a 
 the op stream the CUDA kernel walks, with slots as arrays, and the arithmetic of the reference."""
 import numpy as np
 
-OP_HDR, CH_REC = 5, 3
+OP_HDR, CH_REC = 6, 3
 CH_TIP, CH_INTERNAL, CH_PARTIAL = 0, 1, 2
 
 
@@ -15,9 +15,9 @@ def run_program(prog, nslots, p, pmat_fn):
     for cls in range(K):
         slots = [None] * nslots
         lnsc = np.zeros(N)
-        pc = 2
+        pc = int(prog[3])
         for _ in range(prog[0]):
-            nchild, out_slot, sidx, node, flags = prog[pc:pc + OP_HDR]
+            nchild, out_slot, sidx, node, flags, ntip_op = prog[pc:pc + OP_HDR]
             pc += OP_HDR
             acc = np.ones((N, n))
             for _c in range(nchild):
