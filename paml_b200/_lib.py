@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpaml_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libpaml_b200.so")   # PB200_LIB: A/B builds while tuning
 
 # every symbol include/paml_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

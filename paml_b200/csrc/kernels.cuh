@@ -286,16 +286,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
         int ti = 0;                                          // tips consumed so far
 
         const int* pc = ops;
+        double acc[MT][NT][2];                               // the node being built; survives into the next op (OUT_REG)
         for (int op = 0; op < nops; op++) {
-            const int nchild = pc[0], out_slot = pc[1], sidx = pc[2], ntip_op = pc[5];
+            const int nchild = pc[0], out_slot = pc[1], sidx = pc[2], flags = pc[4], ntip_op = pc[5];
             pc += OP_HDR;
-            double acc[MT][NT][2];
             double tmp[MT][NT][2];
             int c = 0;
+            bool started = false;
+
+            if (flags & OPF_HAS_DIRECT) {
+                // Child 0 was finished by the previous op and is still in `acc` (C-fragment layout).  Its
+                // A fragments are rebuilt with shuffles: element (row g, col 4ks+q) lives in lane
+                // 4g + 2(ks&1) + (q>>1), accumulator pair ks>>1, component q&1.  No shared-memory round trip.
+                const double2* B = reinterpret_cast<const double2*>(Pcls + (size_t)pc[2] * p.pstride) + lane;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) tmp[mt][nt][0] = tmp[mt][nt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    double a[MT], b[2 * C::NTP];
+                    const int sl = (lane & ~3) | ((ks & 1) << 1) | (q >> 1);
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        double lo = __shfl_sync(0xffffffffu, acc[mt][ks >> 1][0], sl);
+                        double hi = __shfl_sync(0xffffffffu, acc[mt][ks >> 1][1], sl);
+                        a[mt] = (q & 1) ? hi : lo;
+                    }
+#pragma unroll
+                    for (int pr = 0; pr < C::NTP; pr++) {
+                        double2 v = __ldg(B + (ks * C::NTP + pr) * 32);
+                        b[2 * pr] = v.x; b[2 * pr + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) dmma884(tmp[mt][nt][0], tmp[mt][nt][1], a[mt], b[nt]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] = tmp[mt][nt][0]; acc[mt][nt][1] = tmp[mt][nt][1]; }
+                started = true;
+                c = 1;
+                pc += CH_REC;
+            }
+
             if (ntip_op > 0) {
-                // Tips first (src/codeml.c:3555-3567): acc[h][j] = PT_a[z_a,h][j] (* PT_b[z_b,h][j]).  The gathers of
-                // up to two tips are issued back to back straight into acc / tmp, so their L2 latency overlaps
-                // and, for a node that also has internal children, hides behind the DMMA work that follows.
+                // Tips (src/codeml.c:3555-3567): acc[h][j] (*)= PT_a[z_a,h][j] (* PT_b[z_b,h][j]).  The gathers of up to
+                // two tips are issued back to back so their latencies overlap.
                 const bool two = (ntip_op > 1);
                 cp_async_wait<C::RING - 2>();
                 __syncwarp();
@@ -314,11 +353,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 ti += two ? 2 : 1;
                 const double* Pm0 = Pcls + (size_t)pc[2] * p.pstride;
                 const double* Pm1 = Pcls + (size_t)pc[two ? CH_REC + 2 : 2] * p.pstride;
+                if (!started) {
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    const double2* row = reinterpret_cast<const double2*>(Pm0 + (size_t)code0[mt] * C::NP);
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double2* row = reinterpret_cast<const double2*>(Pm0 + (size_t)code0[mt] * C::NP);
 #pragma unroll
-                    for (int nt = 0; nt < NT; nt++) { double2 v = ld_gather(row + nt * 4 + q); acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y; }
+                        for (int nt = 0; nt < NT; nt++) { double2 v = ld_gather(row + nt * 4 + q); acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y; }
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const double2* row = reinterpret_cast<const double2*>(Pm0 + (size_t)code0[mt] * C::NP);
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) { double2 v = ld_gather(row + nt * 4 + q); acc[mt][nt][0] *= v.x; acc[mt][nt][1] *= v.y; }
+                    }
                 }
                 if (two) {
 #pragma unroll
@@ -332,10 +381,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) { acc[mt][nt][0] *= tmp[mt][nt][0]; acc[mt][nt][1] *= tmp[mt][nt][1]; }
                 }
-                c = two ? 2 : 1;
-                pc += c * CH_REC;
+                started = true;
+                const int used = two ? 2 : 1;
+                c += used;
+                pc += used * CH_REC;
             }
-            else {
+            if (!started) {
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -367,13 +418,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                         const double2* row = reinterpret_cast<const double2*>(Pm + (size_t)code[mt] * C::NP);
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
-                            double2 v = __ldg(row + nt * 4 + q);
+                            double2 v = ld_gather(row + nt * 4 + q);
                             acc[mt][nt][0] *= v.x; acc[mt][nt][1] *= v.y;
                         }
                     }
                 }
                 else if (kind == CH_INTERNAL) {
-                    // acc[h][j] *= sum_k P[j][k] L_child[h][k]           (src/codeml.c:3568-3575) on DMMA
+                    // a parked child: acc[h][j] *= sum_k P[j][k] L_child[h][k]   (src/codeml.c:3568-3575) on DMMA
                     const double* S = slots + (size_t)idx * C::SLOT_DOUBLES;
                     const double2* B = reinterpret_cast<const double2*>(Pm) + lane;
 #pragma unroll
@@ -440,7 +491,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 }
             }
 
-            if (out_slot >= 0) {
+            if (out_slot == OUT_REG) {
+                // stays in registers: the next op consumes it as its CH_DIRECT child
+            }
+            else if (out_slot >= 0) {
                 double* S = slots + (size_t)out_slot * C::SLOT_DOUBLES;
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++)

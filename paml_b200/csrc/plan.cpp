@@ -63,7 +63,7 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
             std::vector<int> cn;
             for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] > 0) cn.push_back(need[c]); }
             std::sort(cn.begin(), cn.end(), std::greater<int>());
-            int nd = 1;
+            int nd = 0;      // a node whose children are all tips needs no slot: its result stays in registers
             for (size_t i = 0; i < cn.size(); i++) nd = std::max(nd, cn[i] + (i == 0 ? 0 : 1));
             need[v] = nd;
         }
@@ -80,19 +80,26 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
     auto emit_op = [&](int node, const std::vector<Child>& ch, int out_slot, int sidx, int flags) {
         int ntip_op = 0;
         for (const Child& c : ch) ntip_op += (c.kind == CH_TIP);
+        if (!ch.empty() && ch[0].kind == CH_DIRECT) flags |= OPF_HAS_DIRECT;
+        int pos = (int)P.size();
         P.push_back((int)ch.size()); P.push_back(out_slot); P.push_back(sidx); P.push_back(node); P.push_back(flags);
         P.push_back(ntip_op);
         for (const Child& c : ch) { P.push_back(c.kind); P.push_back(c.idx); P.push_back(c.node);
-            if (c.kind == CH_TIP) { out.n_tip_children++; tip_order.push_back(c.idx); } else if (c.kind == CH_INTERNAL) out.n_internal_children++; }
+            if (c.kind == CH_TIP) { out.n_tip_children++; tip_order.push_back(c.idx); }
+            else if (c.kind == CH_INTERNAL || c.kind == CH_DIRECT) out.n_internal_children++; }
         out.nops++;
+        return pos;
     };
 
-    // explicit-stack emission.  result_slot[v] = slot that holds v's vectors once v is done.
-    std::vector<int> result_slot(nnode, -1);
-    struct Frame { int v; std::vector<int> ic; size_t next; int partial; std::vector<Child> pend; };
+    // Explicit-stack emission.  A finished node leaves its vectors in registers (OUT_REG).  The parent either
+    // consumes them at once (CH_DIRECT) or, when it still has to compute another subtree first, parks them: the
+    // child's final op is patched to store into a slot.
+    std::vector<int> final_op(nnode, -1);
+    std::vector<char> done(nnode, 0);
+    struct Frame { int v; std::vector<int> ic; size_t next; int parked, parked_kind, parked_node; bool tips_done; };
     std::vector<Frame> st;
     auto push = [&](int v) {
-        Frame f; f.v = v; f.next = 0; f.partial = -1;
+        Frame f; f.v = v; f.next = 0; f.parked = -1; f.parked_kind = 0; f.parked_node = -1; f.tips_done = false;
         for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] > 0) f.ic.push_back(c); }
         std::stable_sort(f.ic.begin(), f.ic.end(), [&](int a, int b) { return need[a] > need[b]; });
         st.push_back(std::move(f));
@@ -100,37 +107,34 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
     push(root);
     while (!st.empty()) {
         Frame& f = st.back();
-        int v = f.v;
-        size_t m = f.ic.size();
-        // which children does the next op consume?  first op: tips + up to two internal children.
-        if (f.next < m && result_slot[f.ic[f.next]] < 0) { int c = f.ic[f.next]; push(c); continue; }
-        if (f.next < m) {
-            // child f.next is ready
-            int c = f.ic[f.next];
-            f.pend.push_back({CH_INTERNAL, result_slot[c], c});
-            f.next++;
-            bool first_group = (f.partial < 0);
-            // in the first group wait for a second internal child (if any) before emitting
-            if (first_group && f.pend.size() == 1 && f.next < m) continue;
-        }
-        // emit an op with what is pending
+        const int v = f.v;
+        const size_t m = f.ic.size();
         std::vector<Child> ch;
-        if (f.partial < 0)
+        if (f.next < m) {
+            const int c = f.ic[f.next];
+            if (!done[c]) { push(c); continue; }
+            const size_t i = f.next++;
+            if (i == 0 && m >= 2) {                       // park the first (largest) child while the second is computed
+                int s = alloc();
+                P[final_op[c] + 1] = s;
+                f.parked = s; f.parked_kind = CH_INTERNAL; f.parked_node = c;
+                continue;
+            }
+            ch.push_back({CH_DIRECT, 0, c});
+        }
+        if (!f.tips_done) {
             for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] == 0) ch.push_back({CH_TIP, c, c}); }
-        else ch.push_back({CH_PARTIAL, f.partial, v});
-        for (const Child& c : f.pend) ch.push_back(c);
-        bool last = (f.next >= m);
-        for (const Child& c : f.pend) release(c.idx);
-        if (f.partial >= 0) release(f.partial);
-        f.pend.clear();
-        if (!last) {
+            f.tips_done = true;
+        }
+        if (f.parked >= 0) { ch.push_back({f.parked_kind, f.parked, f.parked_node}); release(f.parked); f.parked = -1; }
+        if (f.next < m) {                                  // more subtrees to come: park the running product
             int s = alloc();
             emit_op(v, ch, s, -1, OPF_PARTIAL_OUT);
-            f.partial = s;
+            f.parked = s; f.parked_kind = CH_PARTIAL; f.parked_node = v;
             continue;
         }
-        if (v == root) emit_op(v, ch, -1, -1, 0);
-        else { int s = alloc(); emit_op(v, ch, s, scale_idx[v], 0); result_slot[v] = s; }
+        if (v == root) emit_op(v, ch, OUT_ROOT, -1, 0);
+        else { final_op[v] = emit_op(v, ch, OUT_REG, scale_idx[v], 0); done[v] = 1; }
         st.pop_back();
     }
     out.nslots = std::max<int>(1, (int)used.size());

@@ -8,10 +8,14 @@ namespace pb200 {
 
 // program: [nops, nslots, ntip, first_op_offset] [tip rows in the order the walk consumes them] ops...
 // op header: {nchild, out_slot, scale_idx, node, flags, ntip}; child record: {kind, idx, node};
-// the ntip tip children of an op come first in its child list.
+// child order inside an op: the CH_DIRECT child (if any), then the ntip tips, then slot children.
 enum { PROG_HDR = 4, OP_HDR = 6, CH_REC = 3 };
-enum { CH_TIP = 0, CH_INTERNAL = 1, CH_PARTIAL = 2 };
-enum { OPF_PARTIAL_OUT = 1 };
+// CH_DIRECT: the internal child whose op ran immediately before this one; its vectors are still in the warp's
+// registers and feed the DMMA A operand through shuffles (no shared-memory round trip).  It is always child 0.
+enum { CH_TIP = 0, CH_INTERNAL = 1, CH_PARTIAL = 2, CH_DIRECT = 3 };
+enum { OPF_PARTIAL_OUT = 1, OPF_HAS_DIRECT = 2 };
+// out_slot: >= 0 store to that slot (parked), OUT_ROOT root reduction, OUT_REG keep in registers for the next op
+enum { OUT_ROOT = -1, OUT_REG = -2 };
 
 struct Plan {
     std::vector<int> prog;      // see layout above

@@ -4,7 +4,8 @@ the op stream the CUDA kernel walks, with slots as arrays, and the arithmetic of
 import numpy as np
 
 OP_HDR, CH_REC = 6, 3
-CH_TIP, CH_INTERNAL, CH_PARTIAL = 0, 1, 2
+CH_TIP, CH_INTERNAL, CH_PARTIAL, CH_DIRECT = 0, 1, 2, 3
+OUT_ROOT, OUT_REG = -1, -2
 
 
 def run_program(prog, nslots, p, pmat_fn):
@@ -14,6 +15,7 @@ def run_program(prog, nslots, p, pmat_fn):
     fhK = np.zeros((K, N))
     for cls in range(K):
         slots = [None] * nslots
+        prev = None                      # vectors left "in registers" by the previous op
         lnsc = np.zeros(N)
         pc = int(prog[3])
         for _ in range(prog[0]):
@@ -31,20 +33,29 @@ def run_program(prog, nslots, p, pmat_fn):
                         states = p.charamap[code, :p.nchara[code]]
                         contrib[zs == code] = P[:, states].sum(1)
                     acc *= contrib
+                elif kind == CH_DIRECT:
+                    assert prev is not None and _c == 0, "CH_DIRECT must be child 0 and follow an OUT_REG op"
+                    acc *= prev @ pmat_fn(cls, cnode).T
                 elif kind == CH_INTERNAL:
                     assert slots[idx] is not None, "read of an empty slot"
                     acc *= slots[idx] @ pmat_fn(cls, cnode).T
+                    slots[idx] = None
                 else:
                     assert slots[idx] is not None
                     acc *= slots[idx]
+                    slots[idx] = None
             if sidx >= 0:
                 mx = acc.max(1)
                 tiny = mx < 1e-300
                 acc[tiny] = 1.0
                 acc[~tiny] /= mx[~tiny, None]
                 lnsc += np.where(tiny, -800.0, np.log(np.where(tiny, 1.0, mx)))
+            prev = None
             if out_slot >= 0:
+                assert slots[out_slot] is None, "slot overwritten while live"
                 slots[out_slot] = acc
+            elif out_slot == OUT_REG:
+                prev = acc
             else:
                 fh = acc @ p.pi
                 if p.semantics == 0:

@@ -39,9 +39,9 @@ def test_program_on_synthetic_trees(shape, ns):
     p.nscale, p.scale_flags = likelihood.default_scale_flags(t.nnode, t.root, t.nson, t.sons, 7)
     prog, nslots = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags)
     # slot need is logarithmic for balanced trees and 1-2 for caterpillars
-    assert nslots <= int(np.ceil(np.log2(ns))) + 1
+    assert nslots <= int(np.ceil(np.log2(ns)))
     if shape == "caterpillar":
-        assert nslots <= 2
+        assert nslots <= 1
     r = oracle.lnl(p)
     v, lnf = run_program(prog, nslots, p, _pmat_fn(p))
     assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
@@ -52,7 +52,7 @@ def test_multifurcation_is_folded():
     from paml_b200.tree import parse_newick
     t = parse_newick("((1:.1,2:.1):.1,(3:.1,4:.1):.1,(5:.1,6:.1):.1,(7:.1,8:.1):.1,(9:.1,10:.1):.1,11:.2);")
     prog, nslots = likelihood.plan_tree(t.nnode, t.ns, t.root, t.nson, t.sons, None)
-    assert nslots == 2
+    assert nslots == 1
 
 
 def test_plan_rejects_bad_trees():
