@@ -70,6 +70,10 @@ static int nccl_load()
         if (r_ != 0) return fail("%s failed: %s", #x, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
     } while (0)
 
+// c_prog (constant memory) is one per device: remember whose program it holds
+static const void* g_const_owner[64] = {nullptr};
+static unsigned long long g_const_gen[64] = {0};
+
 // ---- context ----
 struct DevBuf {
     void* p = nullptr;
@@ -105,6 +109,7 @@ struct pb200_ctx {
     // tree
     int nnode = 0, root = -1;
     Plan plan;
+    unsigned long long plan_gen = 0;
     DevBuf d_prog;
     // eval
     DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush;
@@ -168,6 +173,7 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
                       &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush};
     for (DevBuf* b : bufs) b->release();
@@ -289,7 +295,8 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
     if (c->d_prog.ensure(pl.prog.size() * sizeof(int))) return 1;
     CUDA_TRY(cudaMemcpyAsync(c->d_prog.p, pl.prog.data(), pl.prog.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->plan = pl; c->nnode = nnode; c->root = root;
+    static unsigned long long gen_counter = 0;
+    c->plan = pl; c->nnode = nnode; c->root = root; c->plan_gen = ++gen_counter;
     c->have_eval = false;
     return 0;
 }
@@ -350,6 +357,15 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     CUDA_TRY(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PruneParams p;
     p.prog = (const int*)c->d_prog.p;
+    p.prog_in_const = 0;
+    if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
+        if (g_const_owner[c->device] != c || g_const_gen[c->device] != c->plan_gen) {
+            if (g_const_owner[c->device] && g_const_owner[c->device] != c) CUDA_TRY(cudaDeviceSynchronize());   // another context may be using it
+            CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, c->plan.prog.data(), c->plan.prog.size() * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+            g_const_owner[c->device] = c; g_const_gen[c->device] = c->plan_gen;
+        }
+        p.prog_in_const = 1;
+    }
     p.z = (const unsigned char*)c->d_z.p;
     p.zstride = c->zstride; p.npatt = c->npatt;
     p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
@@ -481,8 +497,10 @@ extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double*
     if (ensure_host_stage(c, total) || c->d_stage.ensure(total)) return 1;
     char* hs = (char*)c->h_stage;
     memcpy(hs + off_freq, freqK, (size_t)nclass * 8);
-    memset(hs + off_pi, 0, (size_t)NP * 8);
-    memcpy(hs + off_pi, pi, (size_t)n * 8);
+    for (int ph = 0; ph < NP; ph++) {                      // physical column order (kernels.cuh: phys_to_logical)
+        int j = phys_to_logical(ph);
+        ((double*)(hs + off_pi))[ph] = (j < n) ? pi[j] : 0.0;
+    }
     if (set_stride > 0) memcpy(hs + off_sets, set_data, (size_t)nset * set_stride * 8);
     memcpy(hs + off_t, branch_t, (size_t)nmat * 8);
     {
@@ -652,6 +670,8 @@ extern "C" int pb200_debug_set_program(pb200_ctx* c, const int* prog, int nints,
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->plan.prog.assign(prog, prog + nints);
     c->plan.nops = prog[0]; c->plan.nslots = nslots; c->plan.nscale = nscale;
+    static unsigned long long dbg_gen = 1ull << 62;
+    c->plan_gen = ++dbg_gen;
     return 0;
 }
 

@@ -23,6 +23,13 @@ enum { KIND_UVROOT = 0, KIND_CIJK = 1, KIND_K80 = 2, KIND_JC69LIKE = 3 };
 enum { SEM_LFUN = 0, SEM_LFUNDG = 1 };
 enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2 };
 
+// Physical <-> logical state order inside a conditional vector.  The DMMA C fragment gives lane (g,q) the
+// physical columns 8nt+2q+e (e = 0,1); the A fragment of k-step ks wants column 4ks+q in that lane.  Storing
+// logical state j = 8nt + 4e + q at physical column 8nt + 2q + e makes the two coincide: the accumulators of
+// one DMMA are, register for register, the A operands of the next (k-step 2nt+e), with no shuffle and no
+// shared-memory round trip.  P(t) tiles, tip rows, slots and pi all use the physical order.
+__host__ __device__ __forceinline__ int phys_to_logical(int p) { return (p & ~7) | ((p & 1) << 2) | ((p >> 1) & 3); }
+
 // ------------------------------------------------------------------------------------------------
 // P(t)
 // ------------------------------------------------------------------------------------------------
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
         // PT[code][j] = sum_{k in code} P[j][k]: what a tip in state `code` contributes to parent state j
         // (src/codeml.c:3555-3567); padded parent states j >= n get 0.
         for (int e = tid; e < p.ncodes * NP; e += 256) {
-            int code = e / NP, j = e - code * NP;
+            int code = e / NP, j = phys_to_logical(e - code * NP);
             double v = 0;
             if (j < n) {
                 if (code < n) v = Psm[j * ld + code];
@@ -168,13 +175,13 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
     }
     else {
         // DMMA B-fragment order, two n-tiles per 16-byte element so that one LDG.128 feeds two DMMAs:
-        // element (ks, pr, lane, e) = P[8*(2pr+e) + lane/4][4ks + lane%4]
+        // element (ks, pr, lane, e) = P[j][4ks + lane%4], j = logical state of physical column 8*(2pr+e) + lane/4
         const int NTP = (p.NT + 1) / 2;
         const int total = p.KS * NTP * 64;
         for (int e0 = tid; e0 < total; e0 += 256) {
             int e = e0 & 1, lane = (e0 >> 1) & 31, f = e0 >> 6, pr = f % NTP, ks = f / NTP;
             int nt = 2 * pr + e;
-            int j = 8 * nt + (lane >> 2), k = 4 * ks + (lane & 3);
+            int j = phys_to_logical(8 * nt + (lane >> 2)), k = 4 * ks + (lane & 3);
             out[e0] = (nt < p.NT && j < n && k < n) ? Psm[j * ld + k] : 0.0;
         }
     }
@@ -183,8 +190,14 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
 // ------------------------------------------------------------------------------------------------
 // pruning
 // ------------------------------------------------------------------------------------------------
+// The pruning program of the tree in use: every warp reads it uniformly, op after op, on its critical path,
+// so it lives in constant memory (uniform loads through the constant cache) when it fits.
+#define PB200_CONST_PROG_INTS 12288
+__constant__ int c_prog[PB200_CONST_PROG_INTS];
+
 struct PruneParams {
-    const int* prog;            // plan.h program
+    const int* prog;            // plan.h program in global memory (used when it does not fit c_prog)
+    int prog_in_const;          // 1: read c_prog instead
     const unsigned char* z;     // [ns][zstride] compact codes
     long long zstride, npatt, ntiles, nitems;
     const double* Pbuf;         // [nclass][nnode][pstride]
@@ -226,14 +239,15 @@ struct PruneCfg {
     static constexpr int NP = 8 * NT;                       // padded output states
     static constexpr int KP = 4 * KS;                       // padded input states
     static constexpr int NTP = (NT + 1) / 2;                // n-tile pairs in a B-fragment element
-    // Slot rows: stride % 16 == 8 doubles plus an XOR-4 column swizzle on rows with bit 1 of (row % 8) set
-    // makes BOTH the 8-byte A-fragment loads and the 16-byte C-fragment stores bank-conflict free.
-    static constexpr int STRIDE = ((KP + 7) / 16) * 16 + 8;
+    // Slot rows (physical column order): stride % 16 == 8 doubles, and rows with bit 1 of (row % 8) set keep
+    // each (even, odd) column pair swapped; that makes BOTH the 8-byte A-fragment loads and the 16-byte
+    // C-fragment stores bank-conflict free.
+    static constexpr int STRIDE = ((NP + 7) / 16) * 16 + 8;
     static constexpr int ROWS = 8 * MT;                     // patterns per warp
     static constexpr int SLOT_DOUBLES = ROWS * STRIDE;
     static constexpr int RING = 8;                          // tips whose codes are prefetched ahead
     static constexpr int RING_BYTES = RING * ROWS;
-    static_assert(STRIDE >= KP + 4 || KP % 8 == 0, "swizzled columns must stay inside the row");
+    static_assert(STRIDE >= NP, "a row holds all physical columns");
 };
 
 // One warp owns ROWS site patterns of one site class and walks the whole tree for them; conditional
@@ -248,13 +262,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
     extern __shared__ __align__(16) unsigned char smraw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int xsw = ((g >> 1) & 1) * 4;                     // column swizzle of this lane's rows
+    const int xsw = (g >> 1) & 1;                           // pair-swap swizzle of this lane's rows
     double* slots = reinterpret_cast<double*>(smraw + (size_t)warp * p.warp_smem_bytes);
     unsigned char* ring = reinterpret_cast<unsigned char*>(slots + (size_t)p.nslots * C::SLOT_DOUBLES);
     const long long N = p.npatt;
-    const int nops = p.prog[0], ntip = p.prog[2];
-    const int* tip_order = p.prog + PROG_HDR;
-    const int* ops = p.prog + p.prog[3];
+    const int* prog = p.prog_in_const ? c_prog : p.prog;
+    const int nops = prog[0], ntip = prog[2];
+    const int* tip_order = prog + PROG_HDR;
+    const int* ops = prog + prog[3];
 
     // Warps that share a sub-partition (same warp % 4) share one DMMA pipe.  Started together they stay in
     // lockstep -- all gathering tips at once, then all queueing on the tensor pipe -- and the phases simply add
@@ -295,9 +310,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
             bool started = false;
 
             if (flags & OPF_HAS_DIRECT) {
-                // Child 0 was finished by the previous op and is still in `acc` (C-fragment layout).  Its
-                // A fragments are rebuilt with shuffles: element (row g, col 4ks+q) lives in lane
-                // 4g + 2(ks&1) + (q>>1), accumulator pair ks>>1, component q&1.  No shared-memory round trip.
+                // Child 0 was finished by the previous op and is still in `acc`.  Thanks to the physical column
+                // order (see phys_to_logical) acc[mt][nt][e] IS the A-fragment element of k-step 2nt+e.
                 const double2* B = reinterpret_cast<const double2*>(Pcls + (size_t)pc[2] * p.pstride) + lane;
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++)
@@ -306,13 +320,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 #pragma unroll
                 for (int ks = 0; ks < KS; ks++) {
                     double a[MT], b[2 * C::NTP];
-                    const int sl = (lane & ~3) | ((ks & 1) << 1) | (q >> 1);
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        double lo = __shfl_sync(0xffffffffu, acc[mt][ks >> 1][0], sl);
-                        double hi = __shfl_sync(0xffffffffu, acc[mt][ks >> 1][1], sl);
-                        a[mt] = (q & 1) ? hi : lo;
-                    }
+                    for (int mt = 0; mt < MT; mt++) a[mt] = acc[mt][ks >> 1][ks & 1];
 #pragma unroll
                     for (int pr = 0; pr < C::NTP; pr++) {
                         double2 v = __ldg(B + (ks * C::NTP + pr) * 32);
@@ -435,7 +444,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     for (int ks = 0; ks < KS; ks++) {
                         double a[MT], b[2 * C::NTP];
 #pragma unroll
-                        for (int mt = 0; mt < MT; mt++) a[mt] = S[(8 * mt + g) * C::STRIDE + ((4 * ks + q) ^ xsw)];
+                        for (int mt = 0; mt < MT; mt++) a[mt] = S[(8 * mt + g) * C::STRIDE + ((8 * (ks >> 1) + 2 * q + (ks & 1)) ^ xsw)];
 #pragma unroll
                         for (int pr = 0; pr < C::NTP; pr++) {
                             double2 v = __ldg(B + (ks * C::NTP + pr) * 32);
@@ -458,10 +467,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
-                            if (8 * nt + 2 * q < C::KP) {
-                                double2 v = *reinterpret_cast<const double2*>(S + (8 * mt + g) * C::STRIDE + ((8 * nt + 2 * q) ^ xsw));
-                                acc[mt][nt][0] *= v.x; acc[mt][nt][1] *= v.y;
-                            }
+                            double2 v = *reinterpret_cast<const double2*>(S + (8 * mt + g) * C::STRIDE + 8 * nt + 2 * q);
+                            acc[mt][nt][0] *= xsw ? v.y : v.x; acc[mt][nt][1] *= xsw ? v.x : v.y;
                         }
                 }
             }
@@ -478,8 +485,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     if (mx < 1e-300) {
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) {
-                            acc[mt][nt][0] = (8 * nt + 2 * q     < p.n) ? 1.0 : 0.0;
-                            acc[mt][nt][1] = (8 * nt + 2 * q + 1 < p.n) ? 1.0 : 0.0;
+                            acc[mt][nt][0] = (8 * nt + q     < p.n) ? 1.0 : 0.0;     // logical state of (nt, q, e) is 8nt+4e+q
+                            acc[mt][nt][1] = (8 * nt + 4 + q < p.n) ? 1.0 : 0.0;
                         }
                         lnsc[mt] += -800.0;
                     }
@@ -500,9 +507,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++)
-                        if (8 * nt + 2 * q < C::KP)
-                            *reinterpret_cast<double2*>(S + (8 * mt + g) * C::STRIDE + ((8 * nt + 2 * q) ^ xsw)) =
-                                make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                        *reinterpret_cast<double2*>(S + (8 * mt + g) * C::STRIDE + 8 * nt + 2 * q) =
+                            xsw ? make_double2(acc[mt][nt][1], acc[mt][nt][0]) : make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                 __syncwarp();
             }
             else {
