@@ -12,6 +12,7 @@
 
 #include "../../include/paml_b200.h"
 #include "kernels.cuh"
+#include "prune_tma.cuh"
 #include "plan.h"
 
 using namespace pb200;
@@ -239,6 +240,7 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
     choose_shape(n, &c->NT, &c->KS);
     c->ld = 4 * c->KS;
     c->pstride = std::max<long long>((long long)c->KS * ((c->NT + 1) / 2) * 64, (long long)ncodes * 8 * c->NT);
+    c->pstride = (c->pstride + 15) / 16 * 16;              // tiles are whole 128-byte lines (bulk-copy granularity)
     c->have_eval = false;
     return 0;
 }
@@ -342,8 +344,11 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     PruneLaunch L;
     int warps = 0;
     size_t per_warp = 0;
+    // 61-state shape: 8 patterns per warp x 16 warps (four per sub-partition) hides the tip-gather latency better
+    // than 16 x 8; the small alphabets keep more patterns per warp.  PB200_MT_SMALL=0/1 overrides.
     const char* mtenv = getenv("PB200_MT_SMALL");
-    for (int small = (mtenv && atoi(mtenv)) ? 1 : 0; small < 2 && warps == 0; small++) {
+    const int small0 = mtenv ? (atoi(mtenv) ? 1 : 0) : (c->NT == 8 ? 1 : 0);
+    for (int small = small0; small < 2 && warps == 0; small++) {
         if (pick_launch(c->NT, small, &L)) return 1;
         per_warp = align16((size_t)c->plan.nslots * L.slot_doubles * sizeof(double) + L.ring_bytes);
         size_t budget = smem_budget();
@@ -399,6 +404,94 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     return 0;
 }
 
+// ---- TMA-staged pruning kernel ----
+struct PruneTmaLaunch {
+    void (*fn)(const PruneTmaParams);
+    int rows, slot_doubles, max_warps, ring_bytes;
+};
+template <int NT, int KS, int MT, int MAXW>
+static PruneTmaLaunch make_tma_launch()
+{
+    PruneTmaLaunch L;
+    L.fn = prune_tma_kernel<NT, KS, MT, MAXW>;
+    L.rows = PruneCfg<NT, KS, MT>::ROWS;
+    L.slot_doubles = PruneCfg<NT, KS, MT>::SLOT_DOUBLES;
+    L.max_warps = MAXW;
+    L.ring_bytes = PruneCfg<NT, KS, MT>::RING_BYTES;
+    return L;
+}
+
+static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    PruneTmaLaunch L;
+    const char* mtenv = getenv("PB200_MT_BIG");
+    const bool big = mtenv && atoi(mtenv);
+    if (c->NT == 8) L = big ? make_tma_launch<8, 16, 2, 8>() : make_tma_launch<8, 16, 1, 16>();
+    else if (c->NT == 3) L = big ? make_tma_launch<3, 5, 2, 16>() : make_tma_launch<3, 5, 1, 16>();
+    else if (c->NT == 1) L = make_tma_launch<1, 1, 4, 16>();
+    else return fail("no pruning kernel for NT = %d", c->NT);
+
+    const size_t tile_bytes = (size_t)c->pstride * sizeof(double);          // bytes one bulk copy moves
+    const size_t buf_stride = (tile_bytes + 127) & ~(size_t)127;
+    const size_t per_warp = align16((size_t)c->plan.nslots * L.slot_doubles * sizeof(double) + L.ring_bytes);
+    const size_t bar_bytes = 256, cap = (size_t)227 * 1024;
+    // most warps (a multiple of 4, one per sub-partition) that still leave room for a ring of >= 3 (else >= 2) tiles
+    int warps = 0, nbuf = 0;
+    for (int want_buf = 3; want_buf >= 2 && warps == 0; want_buf--)
+        for (int w = L.max_warps; w >= 4; w -= 4) {
+            size_t fixed = bar_bytes + (size_t)w * per_warp;
+            if (fixed + (size_t)want_buf * buf_stride <= cap) { warps = w; nbuf = (int)std::min<size_t>(8, (cap - fixed) / buf_stride); break; }
+        }
+    if (warps == 0) return fail("pruning kernel: %d slots of %d doubles per warp plus two %zu-byte P(t) tiles do not fit in shared memory",
+                                c->plan.nslots, L.slot_doubles, buf_stride);
+    const char* wenv = getenv("PB200_WARPS");
+    if (wenv && atoi(wenv) >= 4) warps = std::min(warps, atoi(wenv) / 4 * 4);
+    const char* benv = getenv("PB200_NBUF");
+    if (benv && atoi(benv) >= 2) nbuf = std::min(nbuf, atoi(benv));
+    if ((int)c->plan.prog.size() > 5 && nbuf > c->plan.prog[4] && c->plan.prog[4] >= 2) nbuf = c->plan.prog[4];
+    const size_t smem = bar_bytes + (size_t)nbuf * buf_stride + (size_t)warps * per_warp;
+    CUDA_TRY(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    PruneTmaParams pp;
+    PruneParams& p = pp.base;
+    p.prog = (const int*)c->d_prog.p;
+    p.prog_in_const = 0;
+    if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
+        if (g_const_owner[c->device] != c || g_const_gen[c->device] != c->plan_gen) {
+            if (g_const_owner[c->device] && g_const_owner[c->device] != c) CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, c->plan.prog.data(), c->plan.prog.size() * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+            g_const_owner[c->device] = c; g_const_gen[c->device] = c->plan_gen;
+        }
+        p.prog_in_const = 1;
+    }
+    p.z = (const unsigned char*)c->d_z.p;
+    p.zstride = c->zstride; p.npatt = c->npatt;
+    p.ntiles = 0; p.nitems = 0;
+    p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
+    p.nnode = c->nnode; p.nclass = nclass; p.nslots = c->plan.nslots; p.n = c->n;
+    p.semantics = semantics; p.nscale = c->plan.nscale;
+    p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
+    p.tile_counter = (unsigned int*)c->d_counter.p + 4;
+    p.warp_smem_bytes = (int)per_warp;
+    p.stagger_ns = 0;
+    pp.nbuf = nbuf; pp.buf_bytes = (int)tile_bytes; pp.bar_bytes = (int)bar_bytes;
+    // every CTA owns an equal, contiguous share of the patterns (rounded up to 8), processed in chunks of warps*ROWS
+    long long grid_max = c->nsm;
+    const char* genv = getenv("PB200_GRID");
+    if (genv && atoi(genv) > 0) grid_max = atoi(genv);
+    long long rows = (c->npatt + grid_max - 1) / grid_max;
+    rows = (rows + 7) / 8 * 8;
+    pp.rows_per_cta = rows;
+    int grid = (int)((c->npatt + rows - 1) / rows);
+    // NOTE: the kernel addresses tiles with buf_stride == buf_bytes rounded to 128; pass the stride through buf_bytes
+    // only if equal, otherwise fall back to the rounded size for both (source tiles are padded to it below)
+    if (buf_stride != tile_bytes) return fail("internal: P(t) tile of %zu bytes is not a multiple of 128", tile_bytes);
+    L.fn<<<grid, warps * 32, smem, c->stream>>>(pp);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride, const double* d_sets, int nmat,
                      const int* d_mat_set, const double* d_mat_t, double* d_out, long long pstride, int mode, int nnode, int ns,
                      int NT, int KS, int ncodes)
@@ -408,8 +501,9 @@ static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride
     p.kind = kind; p.nr = nr; p.set_stride = set_stride; p.sets = d_sets; p.mat_set = d_mat_set; p.mat_t = d_mat_t;
     p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
     p.out = d_out; p.pstride = pstride; p.mode = mode;
-    size_t smem = (size_t)(kind == KIND_UVROOT ? 2 : 1) * p.ld * p.ld * sizeof(double);
-    pt_kernel<<<nmat, 256, smem, c->stream>>>(p);
+    size_t smem = (kind == KIND_UVROOT ? ((size_t)p.ld * p.ld + 17 * (size_t)p.ld) : 16 * (size_t)p.ld) * sizeof(double);
+    dim3 grid(nmat, (p.ld + 15) / 16);
+    pt_kernel<<<grid, 256, smem, c->stream>>>(p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -448,7 +542,16 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
                   (const double*)(ds + L.off_t), (double*)c->d_P.p, c->pstride, PT_MODE_AUTO, c->nnode, c->ns, c->NT, c->KS, c->ncodes))
         return 1;
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], c->stream));
-    if (launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1;
+    {
+        const char* kenv = getenv("PB200_KERNEL");
+        // default: the warp-independent kernel with P(t) tiles read through L1.  PB200_KERNEL=tma selects the
+        // variant that stages the tiles in shared memory with bulk async copies (correct, currently slower:
+        // its warps move through the matrix ring together, so tip phases and DMMA phases do not overlap).
+        const bool use_l1 = kenv ? strcmp(kenv, "tma") != 0 : true;
+        if (use_l1 ? launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))
+                   : launch_prune_tma(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi)))
+            return 1;
+    }
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], c->stream));
     {
         MixParams mp;

@@ -51,62 +51,54 @@ struct PtParams {
     int mode;           // PT_MODE_*
 };
 
-// One CTA (256 threads) per matrix.  Shared memory: 2*ld*ld doubles (UVROOT) or ld*ld (other kinds).
+// grid = (matrices, row blocks): CTA (m, rb) computes rows [16rb, 16rb+16) of matrix m with 256 threads
+// (thread = one row x four columns) and writes the part of the consumer's layout that those rows feed.
+// Shared memory: ld*ld (V) + 16*ld (scaled U rows) + ld (expm1 terms) doubles for UVROOT, 16*ld otherwise.
 __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
 {
     extern __shared__ __align__(16) double sm[];
-    const int m = blockIdx.x, tid = threadIdx.x, n = p.n, ld = p.ld;
+    const int m = blockIdx.x, rb = blockIdx.y, tid = threadIdx.x, n = p.n, ld = p.ld;
     const int iset = p.mat_set[m];
     if (iset < 0) return;                                   // the root has no branch
+    const int i0 = 16 * rb;
+    if (i0 >= ld) return;
     const double t = p.mat_t[m];
     const double* set = p.sets + (size_t)iset * p.set_stride;
-    double* Psm = sm;                                       // [ld][ld] result, row-major P[i][j]
+    double* Prow = sm;                                      // [16][ld] rows i0.. of the result, P[i][j]
+    const int ty = tid >> 4, tx = tid & 15;                 // row i0+ty, columns tx, tx+16, tx+32, tx+48
 
     if (p.kind == KIND_UVROOT && !(t < 1e-100)) {
         // P = I + sum_k U[:,k] expm1(t Root[k]) V[k,:]   (src/tools.c:529-534)
         const double *Root = set, *U = set + n, *V = set + n + (size_t)n * n;
-        double* Ue = sm;                 // [ld][ld]  U[i][k] * expm1(t*Root[k])
-        double* Vs = sm + ld * ld;       // [ld][ld]
+        double* Ue = sm;                 // [16][ld]   U[i][k] * expm1(t*Root[k]) for this row block (becomes Prow)
+        double* Vs = sm + 16 * ld;       // [ld][ld]
+        double* ex = Vs + ld * ld;       // [ld]
+        for (int k = tid; k < ld; k += 256) ex[k] = (k < n) ? expm1(t * Root[k]) : 0.0;
         for (int e = tid; e < ld * ld; e += 256) {
-            int i = e / ld, k = e - i * ld;
-            bool ok = (i < n && k < n);
-            Ue[e] = ok ? U[i * n + k] * expm1(t * Root[k]) : 0.0;
-            Vs[e] = ok ? V[i * n + k] : 0.0;
+            int k = e / ld, j = e - k * ld;
+            Vs[e] = (k < n && j < n) ? V[k * n + j] : 0.0;
         }
         __syncthreads();
-        const int ty = tid >> 4, tx = tid & 15;
-        double acc[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
-        const bool active = (ty < ld && tx < ld);
-        if (active) {
-            for (int k = 0; k < n; k++) {
-                double u[4], v[4];
-#pragma unroll
-                for (int r = 0; r < 4; r++) { int i = ty + 16 * r; u[r] = (i < ld) ? Ue[i * ld + k] : 0.0; }
-#pragma unroll
-                for (int c = 0; c < 4; c++) { int j = tx + 16 * c; v[c] = (j < ld) ? Vs[k * ld + j] : 0.0; }
-#pragma unroll
-                for (int r = 0; r < 4; r++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) acc[r][c] = fma(u[r], v[c], acc[r][c]);
-            }
+        for (int e = tid; e < 16 * ld; e += 256) {
+            int r = e / ld, k = e - r * ld, i = i0 + r;
+            Ue[e] = (i < n && k < n) ? U[i * n + k] * ex[k] : 0.0;
         }
-        __syncthreads();                 // everyone is done reading Ue/Vs before Psm (= Ue) is overwritten
-        if (active) {
+        __syncthreads();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < n; k++) {
+            const double u = Ue[ty * ld + k];
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) { int j = tx + 16 * c; if (j < ld) acc[c] = fma(u, Vs[k * ld + j], acc[c]); }
+        }
+        __syncthreads();                 // all reads of Ue done before it is overwritten as Prow
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    int i = ty + 16 * r, j = tx + 16 * c;
-                    if (i < ld && j < ld) {
-                        double v = acc[r][c] + (i == j ? 1.0 : 0.0);
-                        if (v < 0) v = 0;                   // src/tools.c:536-537
-                        Psm[i * ld + j] = (i < n && j < n) ? v : 0.0;
-                    }
-                }
+        for (int c = 0; c < 4; c++) {
+            int i = i0 + ty, j = tx + 16 * c;
+            if (j < ld) {
+                double v = acc[c] + (i == j ? 1.0 : 0.0);
+                if (v < 0) v = 0;                           // src/tools.c:536-537
+                Prow[ty * ld + j] = (i < n && j < n) ? v : 0.0;
+            }
         }
     }
     else {
@@ -124,8 +116,8 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
             e1 = 1. / n + (1. - 1. / n) * exp(-n / (n - 1.) * t);
             e2 = (1. - e1) / (n - 1.);
         }
-        for (int e = tid; e < ld * ld; e += 256) {
-            int i = e / ld, j = e - i * ld;
+        for (int e = tid; e < 16 * ld; e += 256) {
+            int r = e / ld, j = e - r * ld, i = i0 + r;
             double v = 0;
             if (i < n && j < n) {
                 if (p.kind == KIND_UVROOT) v = (i == j);    // t < 1e-100 -> identity (src/tools.c:525-528)
@@ -143,38 +135,43 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
                 }
                 else v = (i == j ? e1 : e2);
             }
-            Psm[e] = v;
+            Prow[e] = v;
         }
     }
     __syncthreads();
 
-    // write the matrix in the layout its consumer wants
+    // write this row block's share of the matrix in the layout its consumer wants (Prow[r][k] = P[i0+r][k])
     double* out = p.out + (size_t)m * p.pstride;
     const int node = m % p.nnode;
     const int mode = (p.mode != PT_MODE_AUTO) ? p.mode : (node < p.ns ? PT_MODE_TIP : PT_MODE_FRAG);
     const int NP = 8 * p.NT;
     if (mode == PT_MODE_PLAIN) {
-        for (int e = tid; e < n * n; e += 256) { int i = e / n, j = e - i * n; out[e] = Psm[i * ld + j]; }
+        for (int e = tid; e < 16 * n; e += 256) { int r = e / n, j = e - r * n; if (i0 + r < n) out[(size_t)(i0 + r) * n + j] = Prow[r * ld + j]; }
     }
     else if (mode == PT_MODE_TIP) {
-        // PT[code][j] = sum_{k in code} P[j][k]: what a tip in state `code` contributes to parent state j
-        // (src/codeml.c:3555-3567); padded parent states j >= n get 0.
-        for (int e = tid; e < p.ncodes * NP; e += 256) {
-            int code = e / NP, j = phys_to_logical(e - code * NP);
+        // PT[code][phys(j)] = sum_{k in code} P[j][k]: what a tip in state `code` contributes to parent state j
+        // (src/codeml.c:3555-3567); padded parent states j >= n get 0.  This block owns the parent states i0..i0+15.
+        for (int e = tid; e < p.ncodes * 16; e += 256) {
+            int code = e >> 4, r = e & 15, j = i0 + r;
+            if (j >= NP) continue;
             double v = 0;
             if (j < n) {
-                if (code < n) v = Psm[j * ld + code];
+                if (code < n) v = Prow[r * ld + code];
                 else {
                     const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
                     int cnt = p.amb_n[code - n];
-                    for (int k = 0; k < cnt; k++) v += Psm[j * ld + mp[k]];
+                    for (int k = 0; k < cnt; k++) v += Prow[r * ld + mp[k]];
                 }
             }
-            out[e] = v;
+            // physical position of logical state j (inverse of phys_to_logical)
+            int ph = (j & ~7) | ((j & 3) << 1) | ((j >> 2) & 1);
+            out[(size_t)code * NP + ph] = v;
         }
+        if (rb == 0)                                         // padded parent states beyond ld (none when NP == ld)
+            for (int e = tid; e < p.ncodes * NP; e += 256) { int ph = e % NP; if (phys_to_logical(ph) >= ld) out[e] = 0.0; }
     }
     else {
-        // DMMA B-fragment order, two n-tiles per 16-byte element so that one LDG.128 feeds two DMMAs:
+        // DMMA B-fragment order, two n-tiles per 16-byte element so that one 128-bit load feeds two DMMAs:
         // element (ks, pr, lane, e) = P[j][4ks + lane%4], j = logical state of physical column 8*(2pr+e) + lane/4
         const int NTP = (p.NT + 1) / 2;
         const int total = p.KS * NTP * 64;
@@ -182,7 +179,10 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
             int e = e0 & 1, lane = (e0 >> 1) & 31, f = e0 >> 6, pr = f % NTP, ks = f / NTP;
             int nt = 2 * pr + e;
             int j = phys_to_logical(8 * nt + (lane >> 2)), k = 4 * ks + (lane & 3);
-            out[e0] = (nt < p.NT && j < n && k < n) ? Psm[j * ld + k] : 0.0;
+            bool mine = (j >= i0 && j < i0 + 16);
+            bool pad = (nt >= p.NT || j >= ld);               // entries no row block owns: zero them from block 0
+            if (mine) out[e0] = (nt < p.NT && j < n && k < n) ? Prow[(j - i0) * ld + k] : 0.0;
+            else if (pad && rb == 0) out[e0] = 0.0;
         }
     }
 }

@@ -70,7 +70,7 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
     }
 
     std::vector<int> P;                      // ops only; the header and the tip order are prepended at the end
-    std::vector<int> tip_order;
+    std::vector<int> tip_order, matseq;
     std::vector<char> used;
     auto alloc = [&]() { for (size_t i = 0; i < used.size(); i++) if (!used[i]) { used[i] = 1; return (int)i; }
                          used.push_back(1); return (int)used.size() - 1; };
@@ -85,6 +85,7 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
         P.push_back((int)ch.size()); P.push_back(out_slot); P.push_back(sidx); P.push_back(node); P.push_back(flags);
         P.push_back(ntip_op);
         for (const Child& c : ch) { P.push_back(c.kind); P.push_back(c.idx); P.push_back(c.node);
+            if (c.kind != CH_PARTIAL) matseq.push_back(c.node);
             if (c.kind == CH_TIP) { out.n_tip_children++; tip_order.push_back(c.idx); }
             else if (c.kind == CH_INTERNAL || c.kind == CH_DIRECT) out.n_internal_children++; }
         out.nops++;
@@ -140,8 +141,10 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
     out.nslots = std::max<int>(1, (int)used.size());
     out.prog.clear();
     out.prog.push_back(out.nops); out.prog.push_back(out.nslots);
-    out.prog.push_back((int)tip_order.size()); out.prog.push_back(PROG_HDR + (int)tip_order.size());
+    out.prog.push_back((int)tip_order.size()); out.prog.push_back(PROG_HDR + (int)tip_order.size() + (int)matseq.size());
+    out.prog.push_back((int)matseq.size()); out.prog.push_back(PROG_HDR + (int)tip_order.size());
     out.prog.insert(out.prog.end(), tip_order.begin(), tip_order.end());
+    out.prog.insert(out.prog.end(), matseq.begin(), matseq.end());
     out.prog.insert(out.prog.end(), P.begin(), P.end());
     return "";
 }

@@ -6,10 +6,11 @@
 
 namespace pb200 {
 
-// program: [nops, nslots, ntip, first_op_offset] [tip rows in the order the walk consumes them] ops...
+// program: [nops, nslots, ntip, first_op_offset, nmat, matseq_offset] [tip rows in the order the walk consumes
+// them] [matseq: node ids of the P(t) matrices in the order the walk consumes them (every non-partial child)] ops...
 // op header: {nchild, out_slot, scale_idx, node, flags, ntip}; child record: {kind, idx, node};
 // child order inside an op: the CH_DIRECT child (if any), then the ntip tips, then slot children.
-enum { PROG_HDR = 4, OP_HDR = 6, CH_REC = 3 };
+enum { PROG_HDR = 6, OP_HDR = 6, CH_REC = 3 };
 // CH_DIRECT: the internal child whose op ran immediately before this one; its vectors are still in the warp's
 // registers and feed the DMMA A operand through shuffles (no shared-memory round trip).  It is always child 0.
 enum { CH_TIP = 0, CH_INTERNAL = 1, CH_PARTIAL = 2, CH_DIRECT = 3 };

@@ -14,7 +14,8 @@ ns = p.ns
 internal = [v for v in range(p.nnode) if p.nson[v] > 0 and v != p.root]
 
 def prog_of(ops, tips):
-    out = [len(ops), 2, len(tips), 4 + len(tips)] + list(tips)
+    mats = [k[2] for (children, _) in ops for k in children if k[0] != 2]
+    out = [len(ops), 2, len(tips), 6 + len(tips) + len(mats), len(mats), 6 + len(tips)] + list(tips) + mats
     for (children, out_slot) in ops:
         ntip = sum(1 for k in children if k[0] == 0)
         out += [len(children), out_slot, -1, ns, 0, ntip]
