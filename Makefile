@@ -6,7 +6,29 @@ NVFLAGS = -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
 CSRC    = paml_b200/csrc
 LIB     = paml_b200/libpaml_b200.so
 
-all: $(LIB) oracle
+REF    ?= /root/reference/src
+HOST    = paml_b200/host
+BIN     = paml_b200/bin
+CC     ?= gcc
+
+all: $(LIB) oracle host
+
+# The drop-in programs: the unmodified reference driver (compiled from REF, nothing copied) + our lfun/lfundG.
+# Built only where the reference tree exists; the binaries travel to the GPU box like the .so files do.
+ifneq ($(wildcard $(REF)/codeml.c),)
+host: $(BIN)/codeml_b200 $(BIN)/baseml_b200
+else
+host:
+	@echo "host: reference sources not present at $(REF); using prebuilt $(BIN) if any"
+endif
+
+$(BIN)/tools.o: $(REF)/tools.c
+	@mkdir -p $(BIN)
+	$(CC) -O3 -w -c -o $@ $<
+$(BIN)/codeml_b200: $(HOST)/codeml_b200.c $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
+	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/codeml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
+$(BIN)/baseml_b200: $(HOST)/baseml_b200.c $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
+	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/baseml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
 
 $(LIB): $(CSRC)/api.cu $(CSRC)/kernels.cuh $(CSRC)/plan.cpp $(CSRC)/plan.h include/paml_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/api.cu $(CSRC)/plan.cpp -ldl 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
@@ -19,4 +41,4 @@ clean:
 	rm -f $(LIB) build_ptxas.log
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean host

@@ -59,49 +59,64 @@ def algorithmic_bytes(p):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (1 ms period, in-process thread);
+    falls back to `nvidia-smi -lms` (B200_PROFILING.md recipe) if NVML is unavailable."""
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.rows, self.stop_flag, self.t, self.h = gpu_index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES remaps ordinals; NVML uses physical indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nv is None:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nv is None or self.t is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["NVML unavailable"])
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        nv = self.nv
         try:
-            self.proc.wait(timeout=2)
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                    power_w_max=float(max(power)), samples=len(sm))
+            smax = None
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=smax, reasons=["no samples"])
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown"}
+        reasons = set()
+        for _, _, rs in self.rows:
+            for bit, nm in names.items():
+                if rs & bit:
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median([r[0] for r in self.rows])), sm_max_mhz=smax, reasons=sorted(reasons),
+                    power_w_max=float(max(r[1] for r in self.rows)), samples=len(self.rows))
 
 
 def measured_peaks():
@@ -267,7 +282,6 @@ def main():
     sampler.start()
     res = tl.bench_resident(args.steps, FLUSH)
     barrier()
-    clocks = sampler.stop()
     launches = tl.launch_count() - launches0 - args.steps      # minus the L2-flush launches (outside the timed events)
     dev_ms_total = max_over_ranks(res["step"].sum())
     prune_ms = float(res["prune"].mean()); pt_ms = float(res["pt"].mean()); mix_ms = float(res["mix"].mean())
@@ -282,6 +296,7 @@ def main():
         v = tl.eval_problem(p)              # pack + H2D + kernels (+ all-reduce) + D2H + sync
         e2e_times.append(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop()
     e2e_total = max_over_ranks(sum(e2e_times))
 
     upd_local = p.updates_per_eval()
@@ -313,7 +328,7 @@ def main():
                     kernel_ms=dict(pt=pt_ms, prune=prune_ms, mix_allreduce=mix_ms),
                     neg_lnL=v,
                     roofline=dict(bound="tensor", achieved=ach_tf, peak=fp64_dmma, unit="TFLOP/s", frac=ach_tf / fp64_dmma,
-                                  traffic=None, kernel="prune_kernel<8,16,2>",
+                                  traffic=None, kernel="prune_kernel<8,16,1,16>",
                                   peak_source="FP64 DMMA (mma.sync.m8n8k4.f64) rate measured live by pb200_measure_fp64_peak; "
                                               "MEASURED_PEAKS.json has no FP64 figure (tcgen05 has no FP64 kind)",
                                   flops_per_launch=flops, fp64_dfma_peak=fp64_dfma,

@@ -81,6 +81,14 @@ int pb200_eval(pb200_ctx *ctx, int semantics, int nclass, const double *freqK, i
                int nset, long long set_stride, const double *set_data, const int *branch_set,
                const double *branch_t, const double *pi, double *neg_lnL);
 
+/* The same evaluation split in two, so that one host thread can drive several GPUs (one context each, each
+ * holding a shard of the patterns): _begin packs and enqueues everything on the context's stream and returns
+ * without waiting, _end waits and delivers this context's -lnL (the global one if a communicator is set). */
+int pb200_eval_begin(pb200_ctx *ctx, int semantics, int nclass, const double *freqK, int set_kind, int nr,
+                     int nset, long long set_stride, const double *set_data, const int *branch_set,
+                     const double *branch_t, const double *pi);
+int pb200_eval_end(pb200_ctx *ctx, double *neg_lnL);
+
 /* Per-pattern outputs of the last pb200_eval on this context (this context's shard only):
  *   lnf[npatt]          log f_h, what the reference stores in dfsites[] / prints to `lnf`
  *                       (src/treesub.c:7801-7803, 7655-7656)

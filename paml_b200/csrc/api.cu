@@ -118,7 +118,7 @@ struct pb200_ctx {
     size_t h_stage_cap = 0;
     double* h_result = nullptr;
     int last_nclass = 0;
-    bool have_eval = false;
+    bool have_eval = false, pending = false;
     // parameters of the last evaluation, resident in d_stage (for pb200_bench_resident)
     struct { int semantics, nclass, kind, nr, nmat, mix_blocks; long long set_stride; size_t off_freq, off_pi, off_sets, off_t, off_set; } last = {};
     // comm
@@ -574,11 +574,20 @@ extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double*
                           long long set_stride, const double* set_data, const int* branch_set, const double* branch_t,
                           const double* pi, double* neg_lnL)
 {
+    if (!neg_lnL) return fail("pb200_eval: null argument");
+    if (pb200_eval_begin(c, semantics, nclass, freqK, set_kind, nr, nset, set_stride, set_data, branch_set, branch_t, pi)) return 1;
+    return pb200_eval_end(c, neg_lnL);
+}
+
+extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const double* freqK, int set_kind, int nr, int nset,
+                                long long set_stride, const double* set_data, const int* branch_set, const double* branch_t,
+                                const double* pi)
+{
     if (!c) return fail("pb200_eval: null context");
     if (c->npatt == 0 || c->nnode == 0) return fail("pb200_eval: set_data and set_tree must be called first");
     if (semantics != SEM_LFUN && semantics != SEM_LFUNDG) return fail("pb200_eval: bad semantics");
     if (nclass < 1 || (semantics == SEM_LFUN && nclass != 1)) return fail("pb200_eval: bad nclass %d", nclass);
-    if (!freqK || !branch_set || !branch_t || !pi || !neg_lnL) return fail("pb200_eval: null argument");
+    if (!freqK || !branch_set || !branch_t || !pi) return fail("pb200_eval: null argument");
     if (check_sets(c->n, set_kind, nr, nset, set_stride)) return 1;
     if (set_stride > 0 && !set_data) return fail("pb200_eval: null set_data");
     const int nnode = c->nnode, n = c->n, NP = 8 * c->NT;
@@ -628,9 +637,19 @@ extern "C" int pb200_eval(pb200_ctx* c, int semantics, int nclass, const double*
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *neg_lnL = c->h_result[0];
     c->last_nclass = nclass;
+    c->pending = true;
+    return 0;
+}
+
+extern "C" int pb200_eval_end(pb200_ctx* c, double* neg_lnL)
+{
+    if (!c || !neg_lnL) return fail("pb200_eval_end: null argument");
+    if (!c->pending) return fail("pb200_eval_end: no evaluation in flight");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->pending = false;
+    *neg_lnL = c->h_result[0];
     c->have_eval = true;
     if (c->timing) {
         float ms;
