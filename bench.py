@@ -88,7 +88,7 @@ class ClockSampler:
                 self.rows.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0002)
 
     def start(self):
         if self.nv is None:
