@@ -323,6 +323,8 @@ static PruneLaunch make_launch()
 }
 static int pick_launch(int NT, int mt_small, PruneLaunch* L)
 {
+    const char* renv = getenv("PB200_REGS255");      // tuning: the 8-pattern codon kernel compiled for <= 8 warps (255 registers)
+    if (NT == 8 && mt_small && renv && atoi(renv)) { *L = make_launch<8, 16, 1, 8>(); return 0; }
     if (NT == 8) *L = mt_small ? make_launch<8, 16, 1, 16>() : make_launch<8, 16, 2, 8>();
     else if (NT == 3) *L = mt_small ? make_launch<3, 5, 1, 16>() : make_launch<3, 5, 2, 16>();
     else if (NT == 1) *L = mt_small ? make_launch<1, 1, 1, 16>() : make_launch<1, 1, 4, 16>();
@@ -356,11 +358,22 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
         if (warps == 0 && small == 1) warps = (int)std::min<size_t>(L.max_warps, (size_t)227 * 1024 / per_warp);
     }
     if (warps == 0) return fail("tree needs %d on-chip slots of %d doubles per warp: does not fit in shared memory", c->plan.nslots, L.slot_doubles);
+    // Measured on B200: several small CTAs per SM (4 warps each, one per sub-partition) beat one 16-warp CTA for the
+    // 61-state shape (finer-grained tail, no CTA-wide start-up), so that is the default there.
     const char* wenv = getenv("PB200_WARPS");
     if (wenv && atoi(wenv) > 0) warps = std::min(warps, atoi(wenv));
-    size_t smem = per_warp * warps;
+    else if (c->NT >= 3) warps = std::min(warps, 4);
+    size_t smem = 64 + per_warp * warps;
     CUDA_TRY(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PruneParams p;
+    {
+        const char* lenv = getenv("PB200_PIPE_LOCK");
+        p.pipe_lock = lenv ? atoi(lenv) : 0;
+        const char* senv = getenv("PB200_STATIC_ITEMS");
+        p.static_items = senv ? atoi(senv) : 0;      // measured: the work counter is ~3 % faster than a static deal
+        const char* penv = getenv("PB200_PREFETCH_B");
+        p.prefetch_b = penv ? atoi(penv) : 0;        // measured: explicit L1 prefetch of the next tiles costs more than it hides
+    }
     p.prog = (const int*)c->d_prog.p;
     p.prog_in_const = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
@@ -473,7 +486,7 @@ static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const doubl
     p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
     p.tile_counter = (unsigned int*)c->d_counter.p + 4;
     p.warp_smem_bytes = (int)per_warp;
-    p.stagger_ns = 0;
+    p.stagger_ns = 0; p.pipe_lock = 0; p.static_items = 1; p.prefetch_b = 0;
     pp.nbuf = nbuf; pp.buf_bytes = (int)tile_bytes; pp.bar_bytes = (int)bar_bytes;
     // every CTA owns an equal, contiguous share of the patterns (rounded up to 8), processed in chunks of warps*ROWS
     long long grid_max = c->nsm;

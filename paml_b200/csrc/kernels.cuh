@@ -208,6 +208,9 @@ struct PruneParams {
     unsigned int* tile_counter; // dynamic work distribution (reset by mix_kernel)
     int warp_smem_bytes;        // shared memory per warp: slots + tip-code ring
     unsigned int stagger_ns;    // start delay between the warps that share an SM sub-partition (see kernel)
+    int pipe_lock;              // n > 0: at most n warps of a sub-partition inside a DMMA block at once (tuning aid)
+    int static_items;           // 1: items dealt round-robin to warps; 0: atomic work counter
+    int prefetch_b;             // 1: prefetch.global.L1 the next op's B-fragment tiles one op ahead
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
@@ -263,8 +266,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int xsw = (g >> 1) & 1;                           // pair-swap swizzle of this lane's rows
-    double* slots = reinterpret_cast<double*>(smraw + (size_t)warp * p.warp_smem_bytes);
+    // first 64 bytes: one ticket lock per SM sub-partition (warp % 4)
+    unsigned int* lock_next = reinterpret_cast<unsigned int*>(smraw) + (warp & 3);
+    volatile unsigned int* lock_serving = reinterpret_cast<unsigned int*>(smraw) + 8 + (warp & 3);
+    double* slots = reinterpret_cast<double*>(smraw + 64 + (size_t)warp * p.warp_smem_bytes);
     unsigned char* ring = reinterpret_cast<unsigned char*>(slots + (size_t)p.nslots * C::SLOT_DOUBLES);
+    if (threadIdx.x < 16) reinterpret_cast<unsigned int*>(smraw)[threadIdx.x] = 0u;
+    __syncthreads();
+    // The four (or two) warps of a sub-partition share one DMMA pipe.  Left to the hardware's round-robin they
+    // advance through a DMMA block at a quarter of the speed each and leave it together -- and then all sit in
+    // their tip-gather / store phases at once while the pipe idles (a convoy).  Taking turns instead (one warp owns
+    // the pipe for a whole block, FIFO order) keeps the phases of the warps apart: while one contracts, the others
+    // gather, store or queue.
+    auto pipe_acquire = [&]() {
+        if (!p.pipe_lock) return;
+        if (lane == 0) {
+            const unsigned int ticket = atomicAdd(lock_next, 1u);
+            // pipe_lock = how many warps of the sub-partition may be inside a DMMA block at once
+            while ((int)(ticket - *lock_serving) >= p.pipe_lock) __nanosleep(64);
+        }
+        __syncwarp();
+    };
+    auto pipe_release = [&]() {
+        if (!p.pipe_lock) return;
+        __syncwarp();
+        if (lane == 0) atomicAdd(const_cast<unsigned int*>(lock_serving), 1u);
+    };
     const long long N = p.npatt;
     const int* prog = p.prog_in_const ? c_prog : p.prog;
     const int nops = prog[0], ntip = prog[2];
@@ -279,10 +306,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
         while (wait_ns > 0) { unsigned int chunk = wait_ns > 500000ull ? 500000u : (unsigned int)wait_ns; __nanosleep(chunk); wait_ns -= chunk; }
     }
 
-    for (;;) {
-        unsigned int item_u = 0;
-        if (lane == 0) item_u = atomicAdd(p.tile_counter, 1u);
-        const long long item = __shfl_sync(0xffffffffu, item_u, 0);
+    // Items (pattern tile x class) are dealt round-robin over all warps of the grid: every item costs the same, so a
+    // static deal balances as well as a work counter and keeps its atomic round trip off the critical path.
+    const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long warp_total = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long item = p.static_items ? warp_global : -1;;) {
+        if (!p.static_items) {
+            unsigned int item_u = 0;
+            if (lane == 0) item_u = atomicAdd(p.tile_counter, 1u);
+            item = __shfl_sync(0xffffffffu, item_u, 0);
+        }
         if (item >= p.nitems) break;
         const int cls = (int)(item / p.ntiles);
         const long long h0 = (item - (long long)cls * p.ntiles) * C::ROWS;
@@ -309,6 +342,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
             int c = 0;
             bool started = false;
 
+            if (p.prefetch_b && op + 1 < nops) {
+                // warm L1 with the B-fragment tiles the NEXT op will contract with, one op ahead of their use
+                const int* nx = pc + nchild * CH_REC;            // next op's header
+                const int nnc = nx[0];
+                for (int k = 0; k < nnc; k++) {
+                    const int kd = nx[OP_HDR + k * CH_REC];
+                    if (kd == CH_DIRECT || kd == CH_INTERNAL) {
+                        const char* t0 = reinterpret_cast<const char*>(Pcls + (size_t)nx[OP_HDR + k * CH_REC + 2] * p.pstride);
+                        const int bytes = KS * C::NTP * 64 * (int)sizeof(double);
+                        for (int off = lane * 128; off < bytes; off += 32 * 128)
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(t0 + off));
+                    }
+                }
+            }
+
             if (flags & OPF_HAS_DIRECT) {
                 // Child 0 was finished by the previous op and is still in `acc`.  Thanks to the physical column
                 // order (see phys_to_logical) acc[mt][nt][e] IS the A-fragment element of k-step 2nt+e.
@@ -317,6 +365,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                     for (int nt = 0; nt < NT; nt++) tmp[mt][nt][0] = tmp[mt][nt][1] = 0.0;
+                pipe_acquire();
 #pragma unroll
                 for (int ks = 0; ks < KS; ks++) {
                     double a[MT], b[2 * C::NTP];
@@ -332,6 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 #pragma unroll
                         for (int mt = 0; mt < MT; mt++) dmma884(tmp[mt][nt][0], tmp[mt][nt][1], a[mt], b[nt]);
                 }
+                pipe_release();
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -440,6 +490,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
                         for (int nt = 0; nt < NT; nt++) tmp[mt][nt][0] = tmp[mt][nt][1] = 0.0;
+                    pipe_acquire();
 #pragma unroll
                     for (int ks = 0; ks < KS; ks++) {
                         double a[MT], b[2 * C::NTP];
@@ -455,6 +506,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 #pragma unroll
                             for (int mt = 0; mt < MT; mt++) dmma884(tmp[mt][nt][0], tmp[mt][nt][1], a[mt], b[nt]);
                     }
+                    pipe_release();
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -543,6 +595,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
         }
         cp_async_wait<0>();
         __syncwarp();
+        if (p.static_items) item += warp_total;
     }
 }
 
