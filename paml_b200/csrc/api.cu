@@ -13,6 +13,7 @@
 #include "../../include/paml_b200.h"
 #include "kernels.cuh"
 #include "prune_tma.cuh"
+#include "prune4.cuh"
 #include "plan.h"
 
 using namespace pb200;
@@ -103,7 +104,8 @@ struct pb200_ctx {
     // data
     int n = 0, ns = 0, cleandata = 1, ncodes = 0;
     long long npatt = 0, zstride = 0;
-    DevBuf d_z, d_fpatt, d_amb_n, d_amb_map;
+    DevBuf d_z, d_fpatt, d_amb_n, d_amb_map, d_amb_mask;
+    bool nuc4 = false;          // n == 4: register-resident tree-walk kernel, plain 4x4 P(t) tiles
     // kernel shape
     int NT = 0, KS = 0, ld = 0;
     long long pstride = 0;
@@ -175,7 +177,7 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
-    DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
+    DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
                       &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -236,11 +238,21 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
         CUDA_TRY(cudaMemcpyAsync(c->d_amb_map.p, amb_map.data(), amb_map.size(), cudaMemcpyHostToDevice, c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    {   // 4-state path: per code a bit mask of the states it allows
+        std::vector<unsigned char> mask(256, 0);
+        for (int i = 0; i < n && i < 8; i++) mask[i] = (unsigned char)(1u << i);
+        for (size_t a = 0; a < amb_n.size(); a++)
+            for (int k = 0; k < amb_n[a]; k++) if (amb_map[a * 64 + k] < 8) mask[n + a] |= (unsigned char)(1u << amb_map[a * 64 + k]);
+        if (c->d_amb_mask.ensure(256)) return 1;
+        CUDA_TRY(cudaMemcpy(c->d_amb_mask.p, mask.data(), 256, cudaMemcpyHostToDevice));
+    }
     c->n = n; c->ns = ns; c->npatt = npatt; c->zstride = zstride; c->cleandata = cleandata; c->ncodes = ncodes;
     choose_shape(n, &c->NT, &c->KS);
     c->ld = 4 * c->KS;
     c->pstride = std::max<long long>((long long)c->KS * ((c->NT + 1) / 2) * 64, (long long)ncodes * 8 * c->NT);
     c->pstride = (c->pstride + 15) / 16 * 16;              // tiles are whole 128-byte lines (bulk-copy granularity)
+    c->nuc4 = (n == 4) && !(getenv("PB200_NUC_DMMA") && atoi(getenv("PB200_NUC_DMMA")));
+    if (c->nuc4) c->pstride = std::max(16, ncodes * 4);   // 4x4 P (internal) or PT[code][4] (tip) for the register kernel
     c->have_eval = false;
     return 0;
 }
@@ -505,6 +517,48 @@ static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const doubl
     return 0;
 }
 
+// ---- 4-state register kernel ----
+static int launch_prune4(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    constexpr int PPT = 2, THREADS = 256;
+    Prune4Params p;
+    p.prog = (const int*)c->d_prog.p;
+    p.prog_in_const = 0;
+    if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
+        if (g_const_owner[c->device] != c || g_const_gen[c->device] != c->plan_gen) {
+            if (g_const_owner[c->device] && g_const_owner[c->device] != c) CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, c->plan.prog.data(), c->plan.prog.size() * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+            g_const_owner[c->device] = c; g_const_gen[c->device] = c->plan_gen;
+        }
+        p.prog_in_const = 1;
+    }
+    p.z = (const unsigned char*)c->d_z.p; p.zstride = c->zstride; p.npatt = c->npatt;
+    p.P = (const double*)c->d_P.p; p.pstride = (int)c->pstride; p.nnode = c->nnode; p.nclass = nclass; p.nslots = c->plan.nslots;
+    p.semantics = semantics; p.nscale = c->plan.nscale; p.pi = d_pi;
+    p.amb_mask = (const unsigned char*)c->d_amb_mask.p; p.fhK = (double*)c->d_fhK.p;
+    const size_t slot_bytes = (size_t)c->plan.nslots * PPT * 4 * THREADS * sizeof(double);
+    const size_t p_bytes = (size_t)c->nnode * c->pstride * sizeof(double);
+    p.p_in_smem = (slot_bytes + p_bytes <= (size_t)100 * 1024) ? 1 : 0;      // keep two blocks per SM when possible
+    const size_t z_bytes = (size_t)c->ns * PPT * THREADS;
+    p.ns = c->ns;
+    const char* zenv = getenv("PB200_NUC_ZSMEM");
+    p.z_in_smem = (zenv && atoi(zenv) && slot_bytes + (p.p_in_smem ? p_bytes : 0) + z_bytes <= (size_t)220 * 1024 && c->zstride % 16 == 0) ? 1 : 0;
+    const size_t smem = slot_bytes + (p.p_in_smem ? p_bytes : 0) + (p.z_in_smem ? z_bytes : 0);
+    if (smem > (size_t)227 * 1024) return fail("4-state kernel: %d parked slots do not fit in shared memory", c->plan.nslots);
+    auto fn = p.p_in_smem ? prune4_kernel<PPT, THREADS, true> : prune4_kernel<PPT, THREADS, false>;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long want = (c->npatt + (long long)THREADS * PPT - 1) / ((long long)THREADS * PPT);
+    long long cap = std::max<long long>(1, (long long)c->nsm * per_sm / std::max(1, nclass));
+    dim3 grid((unsigned)std::min<long long>(want, std::max<long long>(cap, 1)), (unsigned)nclass);
+    fn<<<grid, THREADS, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride, const double* d_sets, int nmat,
                      const int* d_mat_set, const double* d_mat_t, double* d_out, long long pstride, int mode, int nnode, int ns,
                      int NT, int KS, int ncodes)
@@ -552,7 +606,7 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
     const auto& L = c->last;
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], c->stream));
     if (launch_pt(c, c->n, L.kind, L.nr, L.set_stride, (const double*)(ds + L.off_sets), L.nmat, (const int*)(ds + L.off_set),
-                  (const double*)(ds + L.off_t), (double*)c->d_P.p, c->pstride, PT_MODE_AUTO, c->nnode, c->ns, c->NT, c->KS, c->ncodes))
+                  (const double*)(ds + L.off_t), (double*)c->d_P.p, c->pstride, c->nuc4 ? PT_MODE_NUC4 : PT_MODE_AUTO, c->nnode, c->ns, c->NT, c->KS, c->ncodes))
         return 1;
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], c->stream));
     {
@@ -561,7 +615,8 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         // variant that stages the tiles in shared memory with bulk async copies (correct, currently slower:
         // its warps move through the matrix ring together, so tip phases and DMMA phases do not overlap).
         const bool use_l1 = kenv ? strcmp(kenv, "tma") != 0 : true;
-        if (use_l1 ? launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))
+        if (c->nuc4) { if (launch_prune4(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
+        else if (use_l1 ? launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))
                    : launch_prune_tma(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi)))
             return 1;
     }
@@ -623,7 +678,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
     char* hs = (char*)c->h_stage;
     memcpy(hs + off_freq, freqK, (size_t)nclass * 8);
     for (int ph = 0; ph < NP; ph++) {                      // physical column order (kernels.cuh: phys_to_logical)
-        int j = phys_to_logical(ph);
+        int j = c->nuc4 ? ph : phys_to_logical(ph);        // the 4-state kernel keeps the logical order
         ((double*)(hs + off_pi))[ph] = (j < n) ? pi[j] : 0.0;
     }
     if (set_stride > 0) memcpy(hs + off_sets, set_data, (size_t)nset * set_stride * 8);

@@ -21,7 +21,7 @@ namespace pb200 {
 
 enum { KIND_UVROOT = 0, KIND_CIJK = 1, KIND_K80 = 2, KIND_JC69LIKE = 3 };
 enum { SEM_LFUN = 0, SEM_LFUNDG = 1 };
-enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2 };
+enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2, PT_MODE_NUC4 = 3 };
 
 // Physical <-> logical state order inside a conditional vector.  The DMMA C fragment gives lane (g,q) the
 // physical columns 8nt+2q+e (e = 0,1); the A fragment of k-step ks wants column 4ks+q in that lane.  Storing
@@ -143,8 +143,26 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
     // write this row block's share of the matrix in the layout its consumer wants (Prow[r][k] = P[i0+r][k])
     double* out = p.out + (size_t)m * p.pstride;
     const int node = m % p.nnode;
-    const int mode = (p.mode != PT_MODE_AUTO) ? p.mode : (node < p.ns ? PT_MODE_TIP : PT_MODE_FRAG);
+    int mode = (p.mode != PT_MODE_AUTO) ? p.mode : (node < p.ns ? PT_MODE_TIP : PT_MODE_FRAG);
     const int NP = 8 * p.NT;
+    if (mode == PT_MODE_NUC4) {
+        // 4-state register kernel (prune4.cuh): internal branch = plain row-major P, tip branch = PT[code][j]
+        if (node >= p.ns) mode = PT_MODE_PLAIN;
+        else {
+            for (int e = tid; e < p.ncodes * 4; e += 256) {
+                int code = e >> 2, j = e & 3;
+                double v = 0;
+                if (code < n) v = Prow[j * ld + code];
+                else {
+                    const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
+                    int cnt = p.amb_n[code - n];
+                    for (int k = 0; k < cnt; k++) v += Prow[j * ld + mp[k]];
+                }
+                out[e] = v;
+            }
+            return;
+        }
+    }
     if (mode == PT_MODE_PLAIN) {
         for (int e = tid; e < 16 * n; e += 256) { int r = e / n, j = e - r * n; if (i0 + r < n) out[(size_t)(i0 + r) * n + j] = Prow[r * ld + j]; }
     }
@@ -293,10 +311,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
         if (lane == 0) atomicAdd(const_cast<unsigned int*>(lock_serving), 1u);
     };
     const long long N = p.npatt;
-    const int* prog = p.prog_in_const ? c_prog : p.prog;
-    const int nops = prog[0], ntip = prog[2];
-    const int* tip_order = prog + PROG_HDR;
-    const int* ops = prog + prog[3];
+    // program words: constant memory (uniform loads) when the program fits there, else read-only global loads; an
+    // explicit branch per access keeps the two address spaces apart (a selected pointer would turn generic)
+    auto PW = [&](int i) -> int { return p.prog_in_const ? c_prog[i] : __ldg(p.prog + i); };
+    const int nops = PW(0), ntip = PW(2);
+    const int ops0 = PW(3);
 
     // Warps that share a sub-partition (same warp % 4) share one DMMA pipe.  Started together they stay in
     // lockstep -- all gathering tips at once, then all queueing on the tensor pipe -- and the phases simply add
@@ -328,15 +347,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
         // prologue of the tip-code ring: the first RING tips of the walk
 #pragma unroll
         for (int i = 0; i < C::RING; i++) {
-            if (i < ntip && lane < C::ROWS / 4) cp_async4(ring + i * C::ROWS + 4 * lane, zt + (size_t)tip_order[i] * p.zstride + 4 * lane);
+            if (i < ntip && lane < C::ROWS / 4) cp_async4(ring + i * C::ROWS + 4 * lane, zt + (size_t)PW(PROG_HDR + i) * p.zstride + 4 * lane);
             cp_async_commit();
         }
         int ti = 0;                                          // tips consumed so far
 
-        const int* pc = ops;
+        int pc = ops0;
         double acc[MT][NT][2];                               // the node being built; survives into the next op (OUT_REG)
         for (int op = 0; op < nops; op++) {
-            const int nchild = pc[0], out_slot = pc[1], sidx = pc[2], flags = pc[4], ntip_op = pc[5];
+            const int nchild = PW(pc), out_slot = PW(pc + 1), sidx = PW(pc + 2), flags = PW(pc + 4), ntip_op = PW(pc + 5);
             pc += OP_HDR;
             double tmp[MT][NT][2];
             int c = 0;
@@ -344,12 +363,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
 
             if (p.prefetch_b && op + 1 < nops) {
                 // warm L1 with the B-fragment tiles the NEXT op will contract with, one op ahead of their use
-                const int* nx = pc + nchild * CH_REC;            // next op's header
-                const int nnc = nx[0];
+                const int nx = pc + nchild * CH_REC;             // next op's header
+                const int nnc = PW(nx);
                 for (int k = 0; k < nnc; k++) {
-                    const int kd = nx[OP_HDR + k * CH_REC];
+                    const int kd = PW(nx + OP_HDR + k * CH_REC);
                     if (kd == CH_DIRECT || kd == CH_INTERNAL) {
-                        const char* t0 = reinterpret_cast<const char*>(Pcls + (size_t)nx[OP_HDR + k * CH_REC + 2] * p.pstride);
+                        const char* t0 = reinterpret_cast<const char*>(Pcls + (size_t)PW(nx + OP_HDR + k * CH_REC + 2) * p.pstride);
                         const int bytes = KS * C::NTP * 64 * (int)sizeof(double);
                         for (int off = lane * 128; off < bytes; off += 32 * 128)
                             asm volatile("prefetch.global.L1 [%0];" :: "l"(t0 + off));
@@ -360,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
             if (flags & OPF_HAS_DIRECT) {
                 // Child 0 was finished by the previous op and is still in `acc`.  Thanks to the physical column
                 // order (see phys_to_logical) acc[mt][nt][e] IS the A-fragment element of k-step 2nt+e.
-                const double2* B = reinterpret_cast<const double2*>(Pcls + (size_t)pc[2] * p.pstride) + lane;
+                const double2* B = reinterpret_cast<const double2*>(Pcls + (size_t)PW(pc + 2) * p.pstride) + lane;
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -406,12 +425,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 for (int k = 0; k < (two ? 2 : 1); k++) {   // refill the ring entries just consumed
                     const int nx = ti + k + C::RING;
                     if (nx < ntip && lane < C::ROWS / 4)
-                        cp_async4(ring + ((ti + k) % C::RING) * C::ROWS + 4 * lane, zt + (size_t)tip_order[nx] * p.zstride + 4 * lane);
+                        cp_async4(ring + ((ti + k) % C::RING) * C::ROWS + 4 * lane, zt + (size_t)PW(PROG_HDR + nx) * p.zstride + 4 * lane);
                     cp_async_commit();
                 }
                 ti += two ? 2 : 1;
-                const double* Pm0 = Pcls + (size_t)pc[2] * p.pstride;
-                const double* Pm1 = Pcls + (size_t)pc[two ? CH_REC + 2 : 2] * p.pstride;
+                const double* Pm0 = Pcls + (size_t)PW(pc + 2) * p.pstride;
+                const double* Pm1 = Pcls + (size_t)PW(pc + (two ? CH_REC + 2 : 2)) * p.pstride;
                 if (!started) {
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
@@ -453,7 +472,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
             }
 
             for (; c < nchild; c++) {
-                const int kind = pc[0], idx = pc[1], node = pc[2];
+                const int kind = PW(pc), idx = PW(pc + 1), node = PW(pc + 2);
                 pc += CH_REC;
                 const double* Pm = Pcls + (size_t)node * p.pstride;
                 if (kind == CH_TIP) {
@@ -468,7 +487,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     {
                         const int nx = ti + C::RING;
                         if (nx < ntip && lane < C::ROWS / 4)
-                            cp_async4(ring + (ti % C::RING) * C::ROWS + 4 * lane, zt + (size_t)tip_order[nx] * p.zstride + 4 * lane);
+                            cp_async4(ring + (ti % C::RING) * C::ROWS + 4 * lane, zt + (size_t)PW(PROG_HDR + nx) * p.zstride + 4 * lane);
                         cp_async_commit();
                     }
                     ti++;
