@@ -319,14 +319,16 @@ static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // ---- pruning kernel dispatch ----
 struct PruneLaunch {
-    void (*fn)(const PruneParams);
+    void (*fn)(const PruneParams);          // program in constant memory
+    void (*fn_g)(const PruneParams);        // program in global memory (too long for c_prog)
     int rows, slot_doubles, max_warps, ring_bytes;
 };
 template <int NT, int KS, int MT, int MAXW>
 static PruneLaunch make_launch()
 {
     PruneLaunch L;
-    L.fn = prune_kernel<NT, KS, MT, MAXW>;
+    L.fn = prune_kernel<NT, KS, MT, MAXW, true>;
+    L.fn_g = prune_kernel<NT, KS, MT, MAXW, false>;
     L.rows = PruneCfg<NT, KS, MT>::ROWS;
     L.slot_doubles = PruneCfg<NT, KS, MT>::SLOT_DOUBLES;
     L.max_warps = MAXW;
@@ -376,7 +378,6 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     if (wenv && atoi(wenv) > 0) warps = std::min(warps, atoi(wenv));
     else if (c->NT >= 3) warps = std::min(warps, 4);
     size_t smem = 64 + per_warp * warps;
-    CUDA_TRY(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PruneParams p;
     {
         const char* lenv = getenv("PB200_PIPE_LOCK");
@@ -396,6 +397,8 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
         }
         p.prog_in_const = 1;
     }
+    void (*kfn)(const PruneParams) = p.prog_in_const ? L.fn : L.fn_g;
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.z = (const unsigned char*)c->d_z.p;
     p.zstride = c->zstride; p.npatt = c->npatt;
     p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
@@ -414,7 +417,7 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
         if (warps <= 4) p.stagger_ns = 0;
     }
     int per_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, L.fn, warps * 32, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
     p.ntiles = (c->npatt + L.rows - 1) / L.rows;
     p.nitems = p.ntiles * nclass;
@@ -423,7 +426,7 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     const char* genv = getenv("PB200_GRID");
     if (genv && atoi(genv) > 0) grid = atoi(genv);
     if (grid < 1) grid = 1;
-    L.fn<<<grid, warps * 32, smem, c->stream>>>(p);
+    kfn<<<grid, warps * 32, smem, c->stream>>>(p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -539,13 +542,13 @@ static int launch_prune4(pb200_ctx* c, int nclass, int semantics, const double* 
     const size_t slot_bytes = (size_t)c->plan.nslots * PPT * 4 * THREADS * sizeof(double);
     const size_t p_bytes = (size_t)c->nnode * c->pstride * sizeof(double);
     p.p_in_smem = (slot_bytes + p_bytes <= (size_t)100 * 1024) ? 1 : 0;      // keep two blocks per SM when possible
-    const size_t z_bytes = (size_t)c->ns * PPT * THREADS;
     p.ns = c->ns;
-    const char* zenv = getenv("PB200_NUC_ZSMEM");
-    p.z_in_smem = (zenv && atoi(zenv) && slot_bytes + (p.p_in_smem ? p_bytes : 0) + z_bytes <= (size_t)220 * 1024 && c->zstride % 16 == 0) ? 1 : 0;
-    const size_t smem = slot_bytes + (p.p_in_smem ? p_bytes : 0) + (p.z_in_smem ? z_bytes : 0);
+    const size_t ring_bytes = (size_t)(THREADS / 32) * 8 * PPT * 32;
+    const size_t smem = slot_bytes + (p.p_in_smem ? p_bytes : 0) + ring_bytes;
     if (smem > (size_t)227 * 1024) return fail("4-state kernel: %d parked slots do not fit in shared memory", c->plan.nslots);
-    auto fn = p.p_in_smem ? prune4_kernel<PPT, THREADS, true> : prune4_kernel<PPT, THREADS, false>;
+    void (*fn)(const Prune4Params) =
+        p.p_in_smem ? (p.prog_in_const ? prune4_kernel<PPT, THREADS, true, true> : prune4_kernel<PPT, THREADS, true, false>)
+                    : (p.prog_in_const ? prune4_kernel<PPT, THREADS, false, true> : prune4_kernel<PPT, THREADS, false, false>);
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, smem));

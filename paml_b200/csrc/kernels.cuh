@@ -276,7 +276,7 @@ struct PruneCfg {
 // memory slots (finished children, [pattern][state] rows).  No block-level synchronisation at all.
 // Tip codes are streamed through a small per-warp cp.async ring a few tips ahead of their use, so the
 // HBM latency of the alignment never sits on the critical path.
-template <int NT, int KS, int MT, int WARPS>
+template <int NT, int KS, int MT, int WARPS, bool CP>
 __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams p)
 {
     using C = PruneCfg<NT, KS, MT>;
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
     const long long N = p.npatt;
     // program words: constant memory (uniform loads) when the program fits there, else read-only global loads; an
     // explicit branch per access keeps the two address spaces apart (a selected pointer would turn generic)
-    auto PW = [&](int i) -> int { return p.prog_in_const ? c_prog[i] : __ldg(p.prog + i); };
+    // (CP is a template parameter so that each instantiation holds exactly one kind of load)
+    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
     const int nops = PW(0), ntip = PW(2);
     const int ops0 = PW(3);
 

@@ -21,14 +21,13 @@ struct Prune4Params {
     int pstride;
     int nnode, nclass, nslots, semantics, nscale;
     int p_in_smem;              // 1: the class's matrices are staged in shared memory
-    int z_in_smem;              // 1: the tip codes of the block's patterns are staged in shared memory, [tip][PPT*THREADS]
     int ns;
     const double* pi;           // [>=4]
     const unsigned char* amb_mask;   // [ncodes]: bit k set = state k compatible with the code (codes 0..3: 1<<code)
     double* fhK;                // [nclass][npatt]
 };
 
-template <int PPT, int THREADS, bool PSM>
+template <int PPT, int THREADS, bool PSM, bool CP>
 __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
 {
     extern __shared__ __align__(16) double sm4[];
@@ -37,7 +36,6 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
     const long long N = p.npatt;
     double* Psm = sm4;                                                   // [nnode][16] (if p_in_smem)
     double* slots = sm4 + (PSM ? (size_t)p.nnode * p.pstride : 0);      // [nslots][PPT][4][THREADS]
-    unsigned char* zs = reinterpret_cast<unsigned char*>(slots + (size_t)p.nslots * PPT * 4 * THREADS);   // [ns][PPT*THREADS]
     const double* Pg = p.P + (size_t)cls * p.nnode * p.pstride;
     if (PSM) {
         for (int e = tid; e < p.nnode * p.pstride; e += THREADS) Psm[e] = Pg[e];
@@ -45,9 +43,13 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
     }
     // program words: constant memory (uniform loads) when the program fits there, else read-only global loads;
     // an explicit branch per access keeps the two address spaces apart (a selected pointer would become generic)
-    auto PW = [&](int i) -> int { return p.prog_in_const ? c_prog[i] : __ldg(p.prog + i); };
-    const int nops = PW(0);
+    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
+    const int nops = PW(0), ntip = PW(2);
     const int ops0 = PW(3);
+    // per-warp ring of tip codes, RING4 tips ahead of their use (cp.async, 4 bytes per lane): [slot][PPT][32]
+    constexpr int RING4 = 8;
+    const int warp = tid >> 5, lane = tid & 31;
+    unsigned char* ring = reinterpret_cast<unsigned char*>(slots + (size_t)p.nslots * PPT * 4 * THREADS) + (size_t)warp * RING4 * PPT * 32;
     const double pi0 = p.pi[0], pi1 = p.pi[1], pi2 = p.pi[2], pi3 = p.pi[3];
 
     for (long long base = (long long)blockIdx.x * THREADS * PPT; base < N; base += (long long)gridDim.x * THREADS * PPT) {
@@ -58,21 +60,19 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
         double acc[PPT][4], lnsc[PPT];
 #pragma unroll
         for (int u = 0; u < PPT; u++) lnsc[u] = 0.0;
-        if (p.z_in_smem) {
-            // stage the tip codes of this block's PPT*THREADS patterns: one coalesced pass, so that no tip of the walk
-            // waits on a dependent global load (zstride and base are multiples of 16, rows are zero padded)
-            __syncthreads();
-            constexpr int ROWB = PPT * THREADS;                       // bytes per tip
-            for (int e = tid * 16; e < p.ns * ROWB; e += THREADS * 16) {
-                const int tip = e / ROWB, off = e - tip * ROWB;
-                const long long src = (long long)tip * p.zstride + base + off;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (base + off + 16 <= p.zstride) v = *reinterpret_cast<const uint4*>(p.z + src);
-                *reinterpret_cast<uint4*>(zs + e) = v;
+        // ring prologue: codes of the first RING4 tips of the walk for this warp's PPT*32 patterns
+        auto ring_fill = [&](int slot, int tipi) {
+            if (tipi < ntip && lane < PPT * 8) {
+                const int u = lane >> 3, l4 = (lane & 7) * 4;
+                const long long hh = base + (long long)u * THREADS + warp * 32 + l4;
+                if (hh + 4 <= p.zstride)
+                    cp_async4(ring + (slot * PPT + u) * 32 + l4, p.z + (size_t)PW(PROG_HDR + tipi) * p.zstride + hh);
             }
-            __syncthreads();
-        }
-
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int i = 0; i < RING4; i++) ring_fill(i, i);
+        int ti = 0;
         int pc = ops0;
         for (int op = 0; op < nops; op++) {
             const int nchild = PW(pc), out_slot = PW(pc + 1), sidx = PW(pc + 2);
@@ -95,9 +95,17 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
                 const double* Pm = (PSM ? Psm : Pg) + (size_t)node * p.pstride;
                 if (kind == CH_TIP) {
                     // tip (src/baseml.c:1547-1558): row `code` of PT[code][j] = sum of the columns of P the code allows
+                    cp_async_wait<RING4 - 1>();
+                    __syncwarp();
+                    int codes[PPT];
+#pragma unroll
+                    for (int u = 0; u < PPT; u++) codes[u] = ring[((ti % RING4) * PPT + u) * 32 + lane];
+                    __syncwarp();
+                    ring_fill(ti % RING4, ti + RING4);
+                    ti++;
 #pragma unroll
                     for (int u = 0; u < PPT; u++) {
-                        const int code = p.z_in_smem ? zs[idx * (PPT * THREADS) + u * THREADS + tid] : p.z[(size_t)idx * p.zstride + h[u]];
+                        const int code = codes[u];
                         double cj[4];
                         {
                             const double2 a = *reinterpret_cast<const double2*>(Pm + code * 4);
@@ -168,6 +176,8 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
                 }
             }
         }
+        cp_async_wait<0>();
+        __syncwarp();
     }
 }
 
