@@ -119,6 +119,16 @@ class ClockSampler:
                     power_w_max=float(max(r[1] for r in self.rows)), samples=len(self.rows))
 
 
+def prune_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pruning kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/r1_prune_traffic.json); None if absent."""
+    try:
+        j = json.load(open(os.path.join(REPO, "profiles", "r1_prune_traffic.json")))
+        return j["dram_bytes_read"] + j["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -328,7 +338,7 @@ def main():
                     kernel_ms=dict(pt=pt_ms, prune=prune_ms, mix_allreduce=mix_ms),
                     neg_lnL=v,
                     roofline=dict(bound="tensor", achieved=ach_tf, peak=fp64_dmma, unit="TFLOP/s", frac=ach_tf / fp64_dmma,
-                                  traffic=None, kernel="prune_kernel<8,16,1,16>",
+                                  traffic=prune_traffic(), kernel="prune_kernel<8,16,1,16,true> (4-warp CTAs)",
                                   peak_source="FP64 DMMA (mma.sync.m8n8k4.f64) rate measured live by pb200_measure_fp64_peak; "
                                               "MEASURED_PEAKS.json has no FP64 figure (tcgen05 has no FP64 kind)",
                                   flops_per_launch=flops, fp64_dfma_peak=fp64_dfma,

@@ -521,9 +521,9 @@ static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const doubl
 }
 
 // ---- 4-state register kernel ----
-static int launch_prune4(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+template <int PPT, int THREADS>
+static int launch_prune4_t(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
 {
-    constexpr int PPT = 2, THREADS = 256;
     Prune4Params p;
     p.prog = (const int*)c->d_prog.p;
     p.prog_in_const = 0;
@@ -560,6 +560,15 @@ static int launch_prune4(pb200_ctx* c, int nclass, int semantics, const double* 
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+static int launch_prune4(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    const char* e = getenv("PB200_NUC_PPT");
+    const int v = e ? atoi(e) : 2;
+    if (v == 4) return launch_prune4_t<4, 128>(c, nclass, semantics, d_pi);
+    if (v == 1) return launch_prune4_t<1, 256>(c, nclass, semantics, d_pi);
+    if (v == 3) return launch_prune4_t<2, 128>(c, nclass, semantics, d_pi);
+    return launch_prune4_t<2, 256>(c, nclass, semantics, d_pi);
 }
 
 static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride, const double* d_sets, int nmat,
