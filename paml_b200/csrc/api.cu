@@ -115,7 +115,8 @@ struct pb200_ctx {
     unsigned long long plan_gen = 0;
     DevBuf d_prog;
     // eval
-    DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush;
+    DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush, d_item_partial;
+    bool fused_last = false;    // the last pruning launch already produced lnf and the sum
     void* h_stage = nullptr;
     size_t h_stage_cap = 0;
     double* h_result = nullptr;
@@ -178,7 +179,7 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
-                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush};
+                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
@@ -421,6 +422,17 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     if (per_sm < 1) per_sm = 1;
     p.ntiles = (c->npatt + L.rows - 1) / L.rows;
     p.nitems = p.ntiles * nclass;
+    {
+        const char* fenv = getenv("PB200_FUSE_LFUN");
+        // measured: fusing lfun's sum into the pruning kernel (last-CTA reduction) costs ~12 us, the separate mixture
+        // kernel ~10 us, so it stays an option (PB200_FUSE_LFUN=1)
+        p.fuse_lfun = (semantics == SEM_LFUN && nclass == 1 && fenv && atoi(fenv)) ? 1 : 0;
+        p.fpatt = (const double*)c->d_fpatt.p; p.lnf = (double*)c->d_lnf.p;
+        p.done_counter = (unsigned int*)c->d_counter.p + 8; p.result = (double*)c->d_result.p;
+        if (p.fuse_lfun && c->d_item_partial.ensure((size_t)p.nitems * sizeof(double))) return 1;
+        p.item_partial = (double*)c->d_item_partial.p;
+        c->fused_last = (p.fuse_lfun != 0);
+    }
     long long want = (p.nitems + warps - 1) / warps;
     int grid = (int)std::min<long long>(want, (long long)c->nsm * per_sm);
     const char* genv = getenv("PB200_GRID");
@@ -627,13 +639,14 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         // variant that stages the tiles in shared memory with bulk async copies (correct, currently slower:
         // its warps move through the matrix ring together, so tip phases and DMMA phases do not overlap).
         const bool use_l1 = kenv ? strcmp(kenv, "tma") != 0 : true;
+        c->fused_last = false;
         if (c->nuc4) { if (launch_prune4(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
         else if (use_l1 ? launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))
                    : launch_prune_tma(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi)))
             return 1;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], c->stream));
-    {
+    if (!c->fused_last) {
         MixParams mp;
         mp.fhK = (const double*)c->d_fhK.p; mp.fpatt = (const double*)c->d_fpatt.p; mp.freqK = (const double*)(ds + L.off_freq);
         mp.lnf = (double*)c->d_lnf.p; mp.partial = (double*)c->d_partial.p; mp.counter = (unsigned int*)c->d_counter.p;

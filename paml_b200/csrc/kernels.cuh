@@ -229,6 +229,14 @@ struct PruneParams {
     int pipe_lock;              // n > 0: at most n warps of a sub-partition inside a DMMA block at once (tuning aid)
     int static_items;           // 1: items dealt round-robin to warps; 0: atomic work counter
     int prefetch_b;             // 1: prefetch.global.L1 the next op's B-fragment tiles one op ahead
+    // lfun fused in (one class, PB200_SEM_LFUN): the root op also writes log f_h, weights it and the kernel ends
+    // with the deterministic sum -- no separate mixture kernel for this case
+    int fuse_lfun;
+    const double* fpatt;        // [npatt]
+    double* lnf;                // [npatt]
+    double* item_partial;       // [nitems]: -sum_h fpatt_h log f_h of each work item (fixed order inside an item)
+    unsigned int* done_counter; // CTAs finished (zero on entry; the last CTA resets it and tile_counter)
+    double* result;             // [1]
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
@@ -609,13 +617,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                             v = p.nscale ? log(fh) + lnsc[mt] : fh;
                         }
                         p.fhK[(size_t)cls * N + h] = v;
+                        if (p.fuse_lfun) {                         // src/treesub.c:7779, 7800-7801
+                            const double w = p.fpatt[h];
+                            const bool on = (w > 0);
+                            p.lnf[h] = on ? v : 0.0;
+                            fh = on ? -v * w : 0.0;
+                        }
+                    }
+                    else fh = 0.0;
+                    if (p.fuse_lfun) {
+                        // sum of the tile's rows in a fixed order (lanes with q == 0 hold rows g = 0..7)
+                        fh += __shfl_xor_sync(0xffffffffu, fh, 4);
+                        fh += __shfl_xor_sync(0xffffffffu, fh, 8);
+                        fh += __shfl_xor_sync(0xffffffffu, fh, 16);
+                        if (mt == 0) lnsc[0] = fh; else lnsc[0] += fh;   // lnsc is dead after the root: reuse as the item's sum
                     }
                 }
+                if (p.fuse_lfun && lane == 0) p.item_partial[item] = lnsc[0];
             }
         }
         cp_async_wait<0>();
         __syncwarp();
         if (p.static_items) item += warp_total;
+    }
+
+    if (p.fuse_lfun) {
+        // The last CTA to finish adds the per-item sums in item order: a fixed-shape reduction, bit-reproducible
+        // from call to call whatever the scheduling was (the optimiser differentiates -lnL numerically).
+        __shared__ double red[32];
+        __shared__ bool last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            double t = 0.0;
+            for (long long i = threadIdx.x; i < p.nitems; i += blockDim.x) t += p.item_partial[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0) red[warp] = t;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double r = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += red[w];
+                p.result[0] = r;
+                *p.done_counter = 0u;
+                *p.tile_counter = 0u;
+            }
+        }
     }
 }
 
