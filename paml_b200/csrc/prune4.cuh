@@ -21,7 +21,7 @@ struct Prune4Params {
     int pstride;
     int nnode, nclass, nslots, semantics, nscale;
     int p_in_smem;              // 1: the class's matrices are staged in shared memory
-    int ns;
+    int ns, ncodes;
     const double* pi;           // [>=4]
     const unsigned char* amb_mask;   // [ncodes]: bit k set = state k compatible with the code (codes 0..3: 1<<code)
     double* fhK;                // [nclass][npatt]
@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
                 const long long hh = base + (long long)u * THREADS + warp * 32 + l4;
                 if (hh + 4 <= p.zstride)
                     cp_async4(ring + (slot * PPT + u) * 32 + l4, p.z + (size_t)PW(PROG_HDR + tipi) * p.zstride + hh);
+                else                                          // past the padded row: dead patterns read state 0
+                    *reinterpret_cast<unsigned int*>(ring + (slot * PPT + u) * 32 + l4) = 0u;
             }
             cp_async_commit();
         };
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
                     __syncwarp();
                     int codes[PPT];
 #pragma unroll
-                    for (int u = 0; u < PPT; u++) codes[u] = ring[((ti % RING4) * PPT + u) * 32 + lane];
+                    for (int u = 0; u < PPT; u++) codes[u] = min((int)ring[((ti % RING4) * PPT + u) * 32 + lane], p.ncodes - 1);
                     __syncwarp();
                     ring_fill(ti % RING4, ti + RING4);
                     ti++;
