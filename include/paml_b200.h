@@ -132,6 +132,13 @@ int pb200_debug_set_program(pb200_ctx *ctx, const int *prog, int nints, int nslo
  * P(t) kernel, pruning kernel, mixture kernel (+ all-reduce when a communicator is set).                   */
 int pb200_bench_resident(pb200_ctx *ctx, int steps, long long flush_bytes, double *ms_step, double *ms_pt,
                          double *ms_prune, double *ms_mix);
+/* End-to-end throughput of the reference-facing call: `steps` times { [flush L2], synchronise, pb200_eval(host
+ * buffers...) } with each pb200_eval timed by the host clock (pack + H2D + kernels + [all-reduce] + D2H + sync);
+ * sec_step[steps] out.  The same as calling pb200_eval in a loop from C, as the drop-in shim does.         */
+int pb200_bench_e2e(pb200_ctx *ctx, int steps, long long flush_bytes, int semantics, int nclass,
+                    const double *freqK, int set_kind, int nr, int nset, long long set_stride,
+                    const double *set_data, const int *branch_set, const double *branch_t, const double *pi,
+                    double *sec_step, double *neg_lnL);
 /* Write `bytes` of device memory (L2 flush between timed iterations). */
 int pb200_flush_l2(pb200_ctx *ctx, long long bytes);
 

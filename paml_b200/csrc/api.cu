@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -920,6 +921,26 @@ extern "C" int pb200_bench_resident(pb200_ctx* c, int steps, long long flush_byt
         }
     for (auto& x : ev) cudaEventDestroy(x);
     return rc;
+}
+
+extern "C" int pb200_bench_e2e(pb200_ctx* c, int steps, long long flush_bytes, int semantics, int nclass, const double* freqK,
+                               int set_kind, int nr, int nset, long long set_stride, const double* set_data, const int* branch_set,
+                               const double* branch_t, const double* pi, double* sec_step, double* neg_lnL)
+{
+    if (!c || steps < 1 || !sec_step) return fail("pb200_bench_e2e: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double v = 0;
+    for (int i = 0; i < steps; i++) {
+        if (flush_bytes > 0) { if (pb200_flush_l2(c, flush_bytes)) return 1; }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        if (pb200_eval(c, semantics, nclass, freqK, set_kind, nr, nset, set_stride, set_data, branch_set, branch_t, pi, &v)) return 1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        sec_step[i] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
+    if (neg_lnL) *neg_lnL = v;
+    return 0;
 }
 
 extern "C" int pb200_flush_l2(pb200_ctx* c, long long bytes)

@@ -172,5 +172,22 @@ class TreeLikelihood:
                                            *[_ptr(a, C.c_double) for a in arrs]))
         return dict(step=arrs[0], pt=arrs[1], prune=arrs[2], mix=arrs[3])
 
+    def bench_e2e(self, p, steps, flush_bytes=0):
+        """Seconds per pb200_eval call (host clock inside the library, host buffers in, -lnL out), `steps` calls."""
+        freqK = np.ascontiguousarray(p.freqK, np.float64)
+        sets = np.ascontiguousarray(p.set_data, np.float64)
+        bset = np.ascontiguousarray(p.branch_set, np.int32)
+        bt = np.ascontiguousarray(p.branch_t, np.float64)
+        pi = np.ascontiguousarray(p.pi, np.float64)
+        sec = np.zeros(steps)
+        out = C.c_double(0)
+        check(self._L.pb200_bench_e2e(self._ctx, C.c_int(steps), C.c_longlong(flush_bytes), C.c_int(p.semantics),
+                                      C.c_int(freqK.shape[0]), _ptr(freqK, C.c_double), C.c_int(p.set_kind), C.c_int(p.nr),
+                                      C.c_int(sets.shape[0]), C.c_longlong(sets.shape[1]), _ptr(sets, C.c_double),
+                                      _ptr(bset, C.c_int), _ptr(bt, C.c_double), _ptr(pi, C.c_double),
+                                      _ptr(sec, C.c_double), C.byref(out)))
+        self.nclass = freqK.shape[0]
+        return sec, out.value
+
     def flush_l2(self, nbytes=256 << 20):
         check(self._L.pb200_flush_l2(self._ctx, C.c_longlong(nbytes)))
