@@ -77,18 +77,18 @@ class ClockSampler:
 
     def _loop(self):
         nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        pw, it = 0.0, 0
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                try:
-                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                rs = get_reasons(self.h)
+                if it % 8 == 0:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 self.rows.append((sm, pw, rs))
+                it += 1
             except Exception:
                 pass
-            time.sleep(0.0002)
 
     def start(self):
         if self.nv is None:
