@@ -256,6 +256,27 @@ def main():
         uid = [TreeLikelihood.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         tl.comm_init(world, rank, uid[0])
+        allreduce = "nccl"
+        if os.environ.get("PB200_ALLREDUCE", "p2p") == "p2p":
+            # fused all-reduce over NVLink peer memory inside the reduction kernel; NCCL stays as the fallback
+            handles = [None] * world
+            dist.all_gather_object(handles, tl.p2p_local_handle())
+            ok = torch.tensor([1], device="cuda")
+            try:
+                tl.p2p_init(world, rank, handles)
+            except Exception as exc:          # e.g. IPC not permitted in this container
+                ok[0] = 0
+                sys.stderr.write("rank %d: p2p all-reduce unavailable (%s); using NCCL\n" % (rank, exc))
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                allreduce = "p2p (fused in mix_kernel, NVLink peer stores)"
+            else:                              # some rank could not map its peers: everybody stays on NCCL
+                try:
+                    tl.p2p_enable(False)
+                except Exception:
+                    pass
+    else:
+        allreduce = "none"
 
     def barrier():
         torch.cuda.synchronize()
@@ -321,7 +342,7 @@ def main():
                     dtype="f64", data="synthetic",
                     config=dict(workload=WORKLOAD, patterns_per_gpu=int(p.npatt), taxa=p.ns, states=p.n, classes=p.nclass,
                                 internal_nodes=p.ninternal, l2="flushed before every timed step (256 MiB write)",
-                                parallelism="site-pattern shards, one process per GPU, one NCCL all-reduce of -lnL per step",
+                                parallelism="site-pattern shards, one process per GPU, one all-reduce of the scalar -lnL per step (%s)" % allreduce,
                                 on_chip_slots=nslots),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,

@@ -107,6 +107,16 @@ int pb200_pmat(pb200_ctx *ctx, int n, int set_kind, int nr, int nset, long long 
 int pb200_nccl_unique_id(char id[128]);
 int pb200_comm_init(pb200_ctx *ctx, int nranks, int rank, const char id[128]);
 
+/* The same all-reduce fused into the reduction kernel over NVLink peer memory (no separate collective launch):
+ * every rank exports a small exchange buffer (CUDA IPC handle, 64 bytes), the launcher all-gathers the handles,
+ * every rank maps its peers' buffers.  From then on the last block of the mixture kernel stores this rank's
+ * partial -lnL into every peer's buffer, waits for theirs and adds them in rank order (bit-identical on all
+ * ranks).  Replaces the NCCL call when initialised; one process per GPU, GPUs connected by NVLink/NVSwitch. */
+int pb200_p2p_local_handle(pb200_ctx *ctx, char handle[64]);
+int pb200_p2p_init(pb200_ctx *ctx, int nranks, int rank, const char *handles /* [nranks][64] */);
+/* Switch between the fused peer-memory all-reduce (1) and the NCCL call (0); all ranks must agree. */
+int pb200_p2p_enable(pb200_ctx *ctx, int enable);
+
 /* Timing / introspection for bench.py and the tests. */
 /* Device time (ms, CUDA events on the context's stream) of the last eval: [0] total, [1] P(t) kernel,
  * [2] pruning kernel, [3] mixture/reduction kernel, [4] all-reduce.  Only filled when timing is enabled. */

@@ -128,6 +128,12 @@ struct pb200_ctx {
     // comm
     nccl_comm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // fused NVLink all-reduce (pb200_p2p_*): this rank's exchange buffer, the peers' buffers as mapped here
+    unsigned long long* xchg = nullptr;
+    void* peer_map[64] = {nullptr};
+    DevBuf d_peer_ptrs;
+    bool p2p = false;
+    unsigned long long eval_seq = 0;
 };
 
 static int ensure_host_stage(pb200_ctx* c, size_t bytes)
@@ -178,9 +184,11 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int r = 0; r < 64; r++) if (c->peer_map[r]) cudaIpcCloseMemHandle(c->peer_map[r]);
+    if (c->xchg) cudaFree(c->xchg);
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
-                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial};
+                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
@@ -401,6 +409,10 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     }
     void (*kfn)(const PruneParams) = p.prog_in_const ? L.fn : L.fn_g;
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const char* cenv = getenv("PB200_CARVEOUT");       // tuning: shared-memory carve-out in percent (rest is L1)
+        if (cenv && atoi(cenv) >= 0) CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cenv)));
+    }
     p.z = (const unsigned char*)c->d_z.p;
     p.zstride = c->zstride; p.npatt = c->npatt;
     p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
@@ -652,13 +664,15 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         mp.fhK = (const double*)c->d_fhK.p; mp.fpatt = (const double*)c->d_fpatt.p; mp.freqK = (const double*)(ds + L.off_freq);
         mp.lnf = (double*)c->d_lnf.p; mp.partial = (double*)c->d_partial.p; mp.counter = (unsigned int*)c->d_counter.p;
         mp.tile_counter = (unsigned int*)c->d_counter.p + 4;
+        mp.peer_xchg = (unsigned long long* const*)c->d_peer_ptrs.p;
+        mp.nranks = c->p2p ? c->nranks : 1; mp.rank = c->rank; mp.seq = ++c->eval_seq;
         mp.result = (double*)c->d_result.p; mp.npatt = c->npatt; mp.nclass = L.nclass; mp.semantics = L.semantics;
         mp.nscale = c->plan.nscale;
         mix_kernel<<<L.mix_blocks, 256, 0, c->stream>>>(mp);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
     }
-    if (c->comm && c->nranks > 1)
+    if (c->comm && c->nranks > 1 && !(c->p2p && !c->fused_last))
         NCCL_TRY(g_nccl.AllReduce(c->d_result.p, c->d_result.p, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
     if (ev) CUDA_TRY(cudaEventRecord(ev[3], c->stream));
     return 0;
@@ -827,6 +841,53 @@ extern "C" int pb200_comm_init(pb200_ctx* c, int nranks, int rank, const char id
     if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
     c->nranks = nranks; c->rank = rank;
+    return 0;
+}
+
+// ---- fused all-reduce over NVLink peer memory ----
+extern "C" int pb200_p2p_local_handle(pb200_ctx* c, char handle[64])
+{
+    if (!c || !handle) return fail("pb200_p2p_local_handle: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->xchg) {
+        CUDA_TRY(cudaMalloc((void**)&c->xchg, 4096));
+        CUDA_TRY(cudaMemset(c->xchg, 0, 4096));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->xchg));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+extern "C" int pb200_p2p_init(pb200_ctx* c, int nranks, int rank, const char* handles)
+{
+    if (!c || !handles) return fail("pb200_p2p_init: null argument");
+    if (nranks < 2 || nranks > 64 || rank < 0 || rank >= nranks) return fail("pb200_p2p_init: bad rank %d / %d", rank, nranks);
+    if (!c->xchg) return fail("pb200_p2p_init: call pb200_p2p_local_handle first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<unsigned long long*> ptrs(nranks, nullptr);
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { ptrs[r] = c->xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* m = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail("pb200_p2p_init: cannot map rank %d's exchange buffer: %s", r, cudaGetErrorString(e));
+        c->peer_map[r] = m;
+        ptrs[r] = (unsigned long long*)m;
+    }
+    if (c->d_peer_ptrs.ensure((size_t)nranks * sizeof(void*))) return 1;
+    CUDA_TRY(cudaMemcpy(c->d_peer_ptrs.p, ptrs.data(), (size_t)nranks * sizeof(void*), cudaMemcpyHostToDevice));
+    c->nranks = nranks; c->rank = rank; c->p2p = true; c->eval_seq = 0;
+    return 0;
+}
+
+extern "C" int pb200_p2p_enable(pb200_ctx* c, int enable)
+{
+    if (!c) return fail("pb200_p2p_enable: null context");
+    if (enable && !c->d_peer_ptrs.p) return fail("pb200_p2p_enable: pb200_p2p_init has not succeeded on this context");
+    c->p2p = (enable != 0);
     return 0;
 }
 

@@ -261,6 +261,18 @@ __device__ __forceinline__ double2 ld_gather(const double2* ptr)
     return v;
 #endif
 }
+// B-fragment tiles are re-read by every warp for every item: ask L1 to keep them (evict-last) while the tip gathers
+// stream past (no-allocate)
+__device__ __forceinline__ double2 ld_bfrag(const double2* ptr)
+{
+#ifdef PB200_BFRAG_EVICT_LAST
+    double2 v;
+    asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+    return v;
+#else
+    return __ldg(ptr);
+#endif
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
 template <int NT, int KS, int MT>
@@ -401,7 +413,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     for (int mt = 0; mt < MT; mt++) a[mt] = acc[mt][ks >> 1][ks & 1];
 #pragma unroll
                     for (int pr = 0; pr < C::NTP; pr++) {
-                        double2 v = __ldg(B + (ks * C::NTP + pr) * 32);
+                        double2 v = ld_bfrag(B + (ks * C::NTP + pr) * 32);
                         b[2 * pr] = v.x; b[2 * pr + 1] = v.y;
                     }
 #pragma unroll
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                         for (int mt = 0; mt < MT; mt++) a[mt] = S[(8 * mt + g) * C::STRIDE + ((8 * (ks >> 1) + 2 * q + (ks & 1)) ^ xsw)];
 #pragma unroll
                         for (int pr = 0; pr < C::NTP; pr++) {
-                            double2 v = __ldg(B + (ks * C::NTP + pr) * 32);
+                            double2 v = ld_bfrag(B + (ks * C::NTP + pr) * 32);
                             b[2 * pr] = v.x; b[2 * pr + 1] = v.y;
                         }
 #pragma unroll
@@ -685,6 +697,11 @@ struct MixParams {
     double* result;         // [1] out: -lnL of this shard
     long long npatt;
     int nclass, semantics, nscale;
+    // fused all-reduce over NVLink peer memory (nranks > 1): every rank owns an exchange buffer
+    // xchg[2 slots][nranks][2 words] that all peers can write; peer_xchg[r] = rank r's buffer as mapped here
+    unsigned long long* const* peer_xchg;
+    int nranks, rank;
+    unsigned long long seq;   // evaluation number (> 0), doubles as the arrival flag
 };
 
 // Block b sums patterns [b*chunk, (b+1)*chunk) in a fixed order; the last block to finish adds the block
@@ -735,7 +752,32 @@ __global__ void __launch_bounds__(256) mix_kernel(const MixParams p)
         red[tid] = t;
         __syncthreads();
         for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
-        if (tid == 0) { p.result[0] = red[0]; *p.counter = 0u; *p.tile_counter = 0u; }
+        if (tid == 0) { *p.counter = 0u; *p.tile_counter = 0u; }
+        if (p.nranks <= 1) { if (tid == 0) p.result[0] = red[0]; }
+        else {
+            // All-reduce of the scalar, fused into this kernel: thread r < nranks stores (value, seq) straight into
+            // rank r's exchange buffer over NVLink, then waits for rank r's own contribution to land here; the sum is
+            // taken in rank order, so every rank gets the same bits.  Slots alternate with the evaluation number: a
+            // peer can only be one evaluation ahead, so two slots are enough.
+            const int slot = (int)(p.seq & 1ull);
+            __shared__ double vals[64];
+            if (tid < p.nranks) {
+                volatile unsigned long long* dst = p.peer_xchg[tid] + ((size_t)slot * p.nranks + p.rank) * 2;
+                dst[0] = (unsigned long long)__double_as_longlong(red[0]);
+                __threadfence_system();
+                dst[1] = p.seq;
+                volatile unsigned long long* src = p.peer_xchg[p.rank] + ((size_t)slot * p.nranks + tid) * 2;
+                while (src[1] != p.seq) { }
+                __threadfence_system();
+                vals[tid] = __longlong_as_double((long long)src[0]);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double r = 0.0;
+                for (int k = 0; k < p.nranks; k++) r += vals[k];
+                p.result[0] = r;
+            }
+        }
     }
 }
 

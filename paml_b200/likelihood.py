@@ -148,6 +148,20 @@ class TreeLikelihood:
     def comm_init(self, nranks, rank, uid):
         check(self._L.pb200_comm_init(self._ctx, C.c_int(nranks), C.c_int(rank), C.c_char_p(uid)))
 
+    def p2p_local_handle(self):
+        buf = C.create_string_buffer(64)
+        check(self._L.pb200_p2p_local_handle(self._ctx, buf))
+        return buf.raw
+
+    def p2p_init(self, nranks, rank, handles):
+        """handles: list of the nranks 64-byte handles in rank order (all-gathered by the launcher)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        check(self._L.pb200_p2p_init(self._ctx, C.c_int(nranks), C.c_int(rank), C.c_char_p(blob)))
+
+    def p2p_enable(self, on=True):
+        check(self._L.pb200_p2p_enable(self._ctx, C.c_int(1 if on else 0)))
+
     # -- timing / introspection -------------------------------------------------------------------
     def set_timing(self, enable=True):
         check(self._L.pb200_set_timing(self._ctx, C.c_int(1 if enable else 0)))

@@ -24,13 +24,22 @@ uid = [TreeLikelihood.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 tl.comm_init(world, rank, uid[0])
 total = tl.eval_problem(p)                      # now ends with one ncclAllReduce of the scalar
+# the same reduction fused into the mixture kernel over NVLink peer memory
+handles = [None] * world
+dist.all_gather_object(handles, tl.p2p_local_handle())
+tl.p2p_init(world, rank, handles)
+totals_p2p = [tl.eval_problem(p) for _ in range(5)]
 parts = [None] * world
 dist.all_gather_object(parts, part)
+allp2p = [None] * world
+dist.all_gather_object(allp2p, totals_p2p[0])
+assert len(set(allp2p)) == 1, "ranks disagree on the fused all-reduce result"
 if rank == 0:
     whole = TreeLikelihood(local)
     whole.set_problem(p)
     ref = whole.eval_problem(p)
     ok = abs(total - ref) <= 1e-12 * abs(ref) and abs(sum(parts) - ref) <= 1e-12 * abs(ref)
+    ok = ok and all(abs(t - ref) <= 1e-12 * abs(ref) for t in totals_p2p) and len(set(totals_p2p)) == 1
     print("MULTI_RANK_RESULT", world, total, ref, sum(parts), "OK" if ok else "MISMATCH")
     whole.close()
 tl.close()
