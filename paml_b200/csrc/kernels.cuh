@@ -70,23 +70,25 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
     if (p.kind == KIND_UVROOT && !(t < 1e-100)) {
         // P = I + sum_k U[:,k] expm1(t Root[k]) V[k,:]   (src/tools.c:529-534)
         const double *Root = set, *U = set + n, *V = set + n + (size_t)n * n;
-        double* Ue = sm;                 // [16][ld]   U[i][k] * expm1(t*Root[k]) for this row block (becomes Prow)
+        double* Ue = sm;                 // [16][ld]   rows i0.. of U (scaled by expm1 on the fly; becomes Prow)
         double* Vs = sm + 16 * ld;       // [ld][ld]
         double* ex = Vs + ld * ld;       // [ld]
+        // one pass of independent global loads (V, this block's rows of U, the expm1 terms), one barrier
         for (int k = tid; k < ld; k += 256) ex[k] = (k < n) ? expm1(t * Root[k]) : 0.0;
         for (int e = tid; e < ld * ld; e += 256) {
             int k = e / ld, j = e - k * ld;
             Vs[e] = (k < n && j < n) ? V[k * n + j] : 0.0;
         }
-        __syncthreads();
         for (int e = tid; e < 16 * ld; e += 256) {
             int r = e / ld, k = e - r * ld, i = i0 + r;
-            Ue[e] = (i < n && k < n) ? U[i * n + k] * ex[k] : 0.0;
+            Ue[e] = (i < n && k < n) ? U[i * n + k] : 0.0;
         }
         __syncthreads();
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* urow = Ue + ty * ld;
+#pragma unroll 4
         for (int k = 0; k < n; k++) {
-            const double u = Ue[ty * ld + k];
+            const double u = urow[k] * ex[k];
 #pragma unroll
             for (int c = 0; c < 4; c++) { int j = tx + 16 * c; if (j < ld) acc[c] = fma(u, Vs[k * ld + j], acc[c]); }
         }
@@ -735,10 +737,15 @@ __global__ void __launch_bounds__(256) mix_kernel(const MixParams p)
         p.lnf[h] = fh;
         s -= fh * w;
     }
-    red[tid] = s;
+    // fixed-shape block sum: butterfly inside each warp, then the 8 warp sums in order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) { if (tid < off) red[tid] += red[tid + off]; __syncthreads(); }
     if (tid == 0) {
+        double b = 0.0;
+        for (int w = 0; w < 8; w++) b += red[w];
+        red[0] = b;
         p.partial[blockIdx.x] = red[0];
         __threadfence();
         unsigned int done = atomicAdd(p.counter, 1u);
