@@ -568,7 +568,7 @@ static int launch_prune4_t(pb200_ctx* c, int nclass, int semantics, const double
     const size_t p_bytes = (size_t)c->nnode * c->pstride * sizeof(double);
     p.p_in_smem = (slot_bytes + p_bytes <= (size_t)100 * 1024) ? 1 : 0;      // keep two blocks per SM when possible
     p.ns = c->ns; p.ncodes = c->ncodes;
-    const size_t ring_bytes = (size_t)(THREADS / 32) * 8 * PPT * 32;
+    const size_t ring_bytes = (size_t)(THREADS / 32) * 16 * PPT * 32;
     const size_t smem = slot_bytes + (p.p_in_smem ? p_bytes : 0) + ring_bytes;
     if (smem > (size_t)227 * 1024) return fail("4-state kernel: %d parked slots do not fit in shared memory", c->plan.nslots);
     void (*fn)(const Prune4Params) =

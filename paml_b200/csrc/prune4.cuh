@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
     auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
     const int nops = PW(0), ntip = PW(2);
     const int ops0 = PW(3);
-    // per-warp ring of tip codes, RING4 tips ahead of their use (cp.async, 4 bytes per lane): [slot][PPT][32]
-    constexpr int RING4 = 8;
+    // per-warp ring of tip codes (cp.async, 4 bytes per lane): [slot][PPT][32], two halves of HALF4 tips; one half is
+    // consumed (no synchronisation per tip) while the other is being refilled, one cp.async group per half
+    constexpr int HALF4 = 8, RING4 = 2 * HALF4;
     const int warp = tid >> 5, lane = tid & 31;
     unsigned char* ring = reinterpret_cast<unsigned char*>(slots + (size_t)p.nslots * PPT * 4 * THREADS) + (size_t)warp * RING4 * PPT * 32;
     const double pi0 = p.pi[0], pi1 = p.pi[1], pi2 = p.pi[2], pi3 = p.pi[3];
@@ -60,20 +61,25 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
         double acc[PPT][4], lnsc[PPT];
 #pragma unroll
         for (int u = 0; u < PPT; u++) lnsc[u] = 0.0;
-        // ring prologue: codes of the first RING4 tips of the walk for this warp's PPT*32 patterns
-        auto ring_fill = [&](int slot, int tipi) {
-            if (tipi < ntip && lane < PPT * 8) {
+        // fill one half of the ring with the codes of tips [tip0, tip0 + HALF4) of the walk: ONE cp.async group
+        auto half_fill = [&](int half, int tip0) {
+            if (lane < PPT * 8) {
                 const int u = lane >> 3, l4 = (lane & 7) * 4;
                 const long long hh = base + (long long)u * THREADS + warp * 32 + l4;
-                if (hh + 4 <= p.zstride)
-                    cp_async4(ring + (slot * PPT + u) * 32 + l4, p.z + (size_t)PW(PROG_HDR + tipi) * p.zstride + hh);
-                else                                          // past the padded row: dead patterns read state 0
-                    *reinterpret_cast<unsigned int*>(ring + (slot * PPT + u) * 32 + l4) = 0u;
+#pragma unroll
+                for (int i = 0; i < HALF4; i++) {
+                    const int tipi = tip0 + i;
+                    if (tipi < ntip) {
+                        unsigned char* dst = ring + ((half * HALF4 + i) * PPT + u) * 32 + l4;
+                        if (hh + 4 <= p.zstride) cp_async4(dst, p.z + (size_t)PW(PROG_HDR + tipi) * p.zstride + hh);
+                        else *reinterpret_cast<unsigned int*>(dst) = 0u;      // past the padded row: dead patterns read state 0
+                    }
+                }
             }
             cp_async_commit();
         };
-#pragma unroll
-        for (int i = 0; i < RING4; i++) ring_fill(i, i);
+        half_fill(0, 0);
+        half_fill(1, HALF4);
         int ti = 0;
         int pc = ops0;
         for (int op = 0; op < nops; op++) {
@@ -97,14 +103,18 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
                 const double* Pm = (PSM ? Psm : Pg) + (size_t)node * p.pstride;
                 if (kind == CH_TIP) {
                     // tip (src/baseml.c:1547-1558): row `code` of PT[code][j] = sum of the columns of P the code allows
-                    cp_async_wait<RING4 - 1>();
-                    __syncwarp();
+                    if (ti % HALF4 == 0) {                    // entering a half: its group (all but the newest) has landed
+                        cp_async_wait<1>();
+                        __syncwarp();
+                    }
                     int codes[PPT];
 #pragma unroll
                     for (int u = 0; u < PPT; u++) codes[u] = min((int)ring[((ti % RING4) * PPT + u) * 32 + lane], p.ncodes - 1);
-                    __syncwarp();
-                    ring_fill(ti % RING4, ti + RING4);
                     ti++;
+                    if (ti % HALF4 == 0) {                    // half consumed: refill it with the tips two halves ahead
+                        __syncwarp();
+                        half_fill(((ti / HALF4) - 1) & 1, ti + HALF4);
+                    }
 #pragma unroll
                     for (int u = 0; u < PPT; u++) {
                         const int code = codes[u];
