@@ -129,6 +129,11 @@ long long pb200_launch_count(pb200_ctx *ctx);
  * of on-chip slots (conditional-vector tiles live at once) in *nslots.                                   */
 int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons,
                     const unsigned char *scale_flags, int *prog, int cap, int *nslots);
+/* The same for the 4-state kernel's macro-op program (csrc/plan.h, Plan4): ops[2 ints per macro-op] and the order
+ * in which the walk consumes the tips.  Returns the number of op ints (negative on error); *ntip_out = tips.  */
+int pb200_plan_tree4(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons,
+                     const unsigned char *scale_flags, int *ops, int cap_ops, int *tip_order, int cap_tips,
+                     int *ntip_out, int *nslots);
 /* FP64 peak micro-benchmark on the context's GPU: tensor (DMMA m8n8k4) and vector (DFMA) TFLOP/s.
  * MEASURED_PEAKS.json has no FP64 figure; bench.py uses this as the FP64 roofline denominator.          */
 int pb200_measure_fp64_peak(pb200_ctx *ctx, double *dmma_tflops, double *dfma_tflops);

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "prune_tma.cuh"
 #include "prune4.cuh"
+#include "prune4v2.cuh"
 #include "plan.h"
 
 using namespace pb200;
@@ -107,6 +108,10 @@ struct pb200_ctx {
     long long npatt = 0, zstride = 0;
     DevBuf d_z, d_fpatt, d_amb_n, d_amb_map, d_amb_mask;
     bool nuc4 = false;          // n == 4: register-resident tree-walk kernel, plain 4x4 P(t) tiles
+    bool nuc4v2 = false;        // ... its macro-op generation (prune4v2.cuh); PB200_NUC_KERNEL=v1 keeps the first one
+    Plan4 plan4;
+    DevBuf d_ops4, d_tip_order, d_zw;
+    bool zw_dirty = true;       // the walk-ordered code packing must be rebuilt (new data or new tree)
     // kernel shape
     int NT = 0, KS = 0, ld = 0;
     long long pstride = 0;
@@ -188,7 +193,8 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->xchg) cudaFree(c->xchg);
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
-                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs};
+                      &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs,
+                      &c->d_ops4, &c->d_tip_order, &c->d_zw};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
@@ -263,6 +269,11 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
     c->pstride = (c->pstride + 15) / 16 * 16;              // tiles are whole 128-byte lines (bulk-copy granularity)
     c->nuc4 = (n == 4) && !(getenv("PB200_NUC_DMMA") && atoi(getenv("PB200_NUC_DMMA")));
     if (c->nuc4) c->pstride = std::max(16, ncodes * 4);   // 4x4 P (internal) or PT[code][4] (tip) for the register kernel
+    {
+        const char* kenv = getenv("PB200_NUC_KERNEL");
+        c->nuc4v2 = c->nuc4 && !(kenv && strcmp(kenv, "v1") == 0);
+        c->zw_dirty = true;
+    }
     c->have_eval = false;
     return 0;
 }
@@ -276,6 +287,20 @@ extern "C" int pb200_plan_tree(int nnode, int ns, int root, const int* nson, con
     if (nslots) *nslots = pl.nslots;
     if (prog) for (int i = 0; i < cap && i < (int)pl.prog.size(); i++) prog[i] = pl.prog[i];
     return (int)pl.prog.size();
+}
+
+extern "C" int pb200_plan_tree4(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                                const unsigned char* scale_flags, int* ops, int cap_ops, int* tip_order, int cap_tips,
+                                int* ntip_out, int* nslots)
+{
+    Plan4 pl;
+    std::string err = plan_tree4(nnode, ns, root, nson, sons, maxsons, scale_flags, pl);
+    if (!err.empty()) { fail("%s", err.c_str()); return -1; }
+    if (nslots) *nslots = pl.nslots;
+    if (ntip_out) *ntip_out = (int)pl.tip_order.size();
+    if (ops) for (int i = 0; i < cap_ops && i < (int)pl.ops.size(); i++) ops[i] = pl.ops[i];
+    if (tip_order) for (int i = 0; i < cap_tips && i < (int)pl.tip_order.size(); i++) tip_order[i] = pl.tip_order[i];
+    return (int)pl.ops.size();
 }
 
 extern "C" int pb200_default_scale_flags(int nnode, int root, const int* nson, const int* sons, int maxsons, int every,
@@ -319,6 +344,17 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
     if (c->d_prog.ensure(pl.prog.size() * sizeof(int))) return 1;
     CUDA_TRY(cudaMemcpyAsync(c->d_prog.p, pl.prog.data(), pl.prog.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->nuc4) {
+        Plan4 p4;
+        err = plan_tree4(nnode, c->ns, root, nson, sons, maxsons, scale_flags, p4);
+        if (!err.empty()) return fail("%s", err.c_str());
+        if (c->d_ops4.ensure(p4.ops.size() * sizeof(int)) || c->d_tip_order.ensure(p4.tip_order.size() * sizeof(int) + 16)) return 1;
+        CUDA_TRY(cudaMemcpyAsync(c->d_ops4.p, p4.ops.data(), p4.ops.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_tip_order.p, p4.tip_order.data(), p4.tip_order.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->plan4 = p4;
+        c->zw_dirty = true;
+    }
     static unsigned long long gen_counter = 0;
     c->plan = pl; c->nnode = nnode; c->root = root; c->plan_gen = ++gen_counter;
     c->have_eval = false;
@@ -596,6 +632,71 @@ static int launch_prune4(pb200_ctx* c, int nclass, int semantics, const double* 
     return launch_prune4_t<2, 256>(c, nclass, semantics, d_pi);
 }
 
+// ---- 4-state macro-op kernel (prune4v2.cuh) ----
+template <int PPT, int THREADS, int MINB>
+static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    const Plan4& pl = c->plan4;
+    const int ntip = (int)pl.tip_order.size(), ngroups = (ntip + 3) / 4;
+    if (c->zw_dirty) {
+        // walk-ordered packing of the tip codes: once per (data, tree)
+        if (c->d_zw.ensure((size_t)ngroups * c->zstride * sizeof(unsigned int))) return 1;
+        long long total = (long long)ngroups * c->zstride;
+        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->nsm * 16);
+        pack_tips4_kernel<<<blocks, 256, 0, c->stream>>>((const unsigned char*)c->d_z.p, c->zstride, (const int*)c->d_tip_order.p, ntip,
+                                                          ngroups, (unsigned int*)c->d_zw.p);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        c->zw_dirty = false;
+    }
+    Prune4v2Params p;
+    p.ops = (const int*)c->d_ops4.p; p.nops = (int)pl.ops.size() / 2;
+    bool in_const = false;
+    if (pl.ops.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
+        if (g_const_owner[c->device] != c || g_const_gen[c->device] != c->plan_gen) {
+            if (g_const_owner[c->device] && g_const_owner[c->device] != c) CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, pl.ops.data(), pl.ops.size() * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+            g_const_owner[c->device] = c; g_const_gen[c->device] = c->plan_gen;
+        }
+        in_const = true;
+    }
+    p.zw = (const unsigned int*)c->d_zw.p; p.zwstride = c->zstride; p.npatt = c->npatt; p.ngroups = ngroups;
+    p.P = (const double*)c->d_P.p; p.pstride = (int)c->pstride; p.nnode = c->nnode; p.nclass = nclass; p.nslots = pl.nslots;
+    p.semantics = semantics; p.nscale = c->plan.nscale; p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
+    const size_t slot_bytes = (size_t)pl.nslots * PPT * 2 * THREADS * sizeof(double2);
+    const size_t p_bytes = (size_t)c->nnode * c->pstride * sizeof(double);
+    const bool psm = slot_bytes + p_bytes <= (size_t)(MINB >= 2 ? 100 : 200) * 1024;
+    const size_t smem = slot_bytes + (psm ? p_bytes : 0);
+    if (smem > (size_t)227 * 1024) return fail("4-state kernel: %d parked slots do not fit in shared memory", pl.nslots);
+    void (*fn)(const Prune4v2Params) =
+        psm ? (in_const ? prune4v2_kernel<PPT, THREADS, MINB, true, true> : prune4v2_kernel<PPT, THREADS, MINB, true, false>)
+            : (in_const ? prune4v2_kernel<PPT, THREADS, MINB, false, true> : prune4v2_kernel<PPT, THREADS, MINB, false, false>);
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long want = (c->npatt + (long long)THREADS * PPT - 1) / ((long long)THREADS * PPT);
+    long long cap = std::max<long long>(1, (long long)c->nsm * per_sm / std::max(1, nclass));
+    const char* genv = getenv("PB200_GRID");
+    if (genv && atoi(genv) > 0) cap = atoi(genv);
+    dim3 grid((unsigned)std::min<long long>(want, cap), (unsigned)nclass);
+    fn<<<grid, THREADS, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int launch_prune4v2(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    const char* e = getenv("PB200_NUC_PPT");
+    const int v = e ? atoi(e) : 2;
+    if (v == 1) return launch_prune4v2_t<1, 256, 3>(c, nclass, semantics, d_pi);
+    if (v == 4) return launch_prune4v2_t<4, 128, 2>(c, nclass, semantics, d_pi);
+    if (v == 41) return launch_prune4v2_t<4, 256, 1>(c, nclass, semantics, d_pi);
+    if (v == 21) return launch_prune4v2_t<2, 128, 4>(c, nclass, semantics, d_pi);
+    if (v == 3) return launch_prune4v2_t<3, 128, 3>(c, nclass, semantics, d_pi);
+    return launch_prune4v2_t<2, 256, 2>(c, nclass, semantics, d_pi);
+}
+
 static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride, const double* d_sets, int nmat,
                      const int* d_mat_set, const double* d_mat_t, double* d_out, long long pstride, int mode, int nnode, int ns,
                      int NT, int KS, int ncodes)
@@ -653,7 +754,8 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         // its warps move through the matrix ring together, so tip phases and DMMA phases do not overlap).
         const bool use_l1 = kenv ? strcmp(kenv, "tma") != 0 : true;
         c->fused_last = false;
-        if (c->nuc4) { if (launch_prune4(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
+        if (c->nuc4v2) { if (launch_prune4v2(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
+        else if (c->nuc4) { if (launch_prune4(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
         else if (use_l1 ? launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))
                    : launch_prune_tma(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi)))
             return 1;

@@ -17,8 +17,7 @@
 
 namespace pb200 {
 
-std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
-                      const unsigned char* scale_flags, Plan& out)
+static std::string check_tree(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons)
 {
     if (nnode < 2 || ns < 1 || ns >= nnode) return "plan_tree: bad nnode/ns";
     if (root < ns || root >= nnode) return "plan_tree: root must be an internal node";
@@ -38,6 +37,16 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
             for (int j = 0; j < nson[i]; j++) seen[sons[i * maxsons + j]]++;
         for (int i = 0; i < nnode; i++)
             if ((i == root && seen[i] != 0) || (i != root && seen[i] != 1)) return "plan_tree: not a tree";
+    }
+    return "";
+}
+
+std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                      const unsigned char* scale_flags, Plan& out)
+{
+    {
+        std::string e = check_tree(nnode, ns, root, nson, sons, maxsons);
+        if (!e.empty()) return e;
     }
     std::vector<int> scale_idx(nnode, -1);
     out = Plan();
@@ -146,6 +155,104 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
     out.prog.insert(out.prog.end(), tip_order.begin(), tip_order.end());
     out.prog.insert(out.prog.end(), matseq.begin(), matseq.end());
     out.prog.insert(out.prog.end(), P.begin(), P.end());
+    return "";
+}
+
+// Macro-op program of the 4-state kernel (see plan.h).  Same Sethi-Ullman ordering as above; what is parked is
+// always the running product of the PARENT (the child's vector already multiplied by its branch matrix), so one
+// slot per pending node is enough and the kernel's register state is a single vector per pattern.
+std::string plan_tree4(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                       const unsigned char* scale_flags, Plan4& out)
+{
+    {
+        std::string e = check_tree(nnode, ns, root, nson, sons, maxsons);
+        if (!e.empty()) return e;
+    }
+    if (nnode >= 65536) return "plan_tree4: more than 65535 nodes";
+    out = Plan4();
+    std::vector<char> scaled(nnode, 0);
+    if (scale_flags)
+        for (int i = 0; i < nnode; i++)
+            if (scale_flags[i] && i != root && i >= ns) { scaled[i] = 1; out.nscale++; }
+
+    std::vector<int> need(nnode, 0);
+    {
+        std::vector<int> order;
+        std::vector<std::pair<int, int>> st;
+        st.push_back({root, 0});
+        while (!st.empty()) {
+            int v = st.back().first, k = st.back().second;
+            if (k < nson[v]) {
+                st.back().second++;
+                int c = sons[v * maxsons + k];
+                if (nson[c] > 0) st.push_back({c, 0});
+            }
+            else { order.push_back(v); st.pop_back(); }
+        }
+        for (int v : order) {
+            std::vector<int> cn;
+            for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] > 0) cn.push_back(need[c]); }
+            std::sort(cn.begin(), cn.end(), std::greater<int>());
+            int nd = 0;
+            for (size_t i = 0; i < cn.size(); i++) nd = std::max(nd, cn[i] + (i == 0 ? 0 : 1));
+            need[v] = nd;
+        }
+    }
+
+    std::vector<char> used;
+    auto alloc = [&]() { for (size_t i = 0; i < used.size(); i++) if (!used[i]) { used[i] = 1; return (int)i; }
+                         used.push_back(1); return (int)used.size() - 1; };
+    auto emit = [&](int opc, int slot, int a, int b) {
+        out.ops.push_back(opc | (slot << 8));
+        out.ops.push_back((a & 0xffff) | (b << 16));
+    };
+    struct Frame { int v; std::vector<int> ic, tips; size_t i; int slot; bool child_done; };
+    std::vector<Frame> st;
+    auto push = [&](int v) {
+        Frame f; f.v = v; f.i = 0; f.slot = -1; f.child_done = false;
+        for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; (nson[c] > 0 ? f.ic : f.tips).push_back(c); }
+        std::stable_sort(f.ic.begin(), f.ic.end(), [&](int a, int b) { return need[a] > need[b]; });
+        st.push_back(std::move(f));
+    };
+    push(root);
+    while (!st.empty()) {
+        Frame& f = st.back();
+        const size_t k = f.ic.size();
+        size_t first_tip = 0;
+        bool finished = false;
+        if (k == 0) {
+            if (f.tips.size() < 2) return "plan_tree4: internal node with fewer than two children";
+            emit(M4_CHERRY, 0, f.tips[0], f.tips[1]);
+            out.tip_order.push_back(f.tips[0]); out.tip_order.push_back(f.tips[1]);
+            first_tip = 2; finished = true;
+        }
+        else if (!f.child_done) { f.child_done = true; int c = f.ic[f.i]; push(c); continue; }
+        else if (k == 1) {
+            if (f.tips.empty()) return "plan_tree4: internal node with a single child";
+            emit(M4_MV_TIP, 0, f.ic[0], f.tips[0]);
+            out.tip_order.push_back(f.tips[0]);
+            first_tip = 1; finished = true;
+        }
+        else if (f.i == 0) {
+            f.slot = alloc();
+            emit(M4_MV_PUSH, f.slot, f.ic[0], 0);
+            f.i = 1; f.child_done = false;
+            continue;
+        }
+        else {
+            emit(M4_MV_POP, f.slot, f.ic[f.i], 0);
+            if (f.i + 1 < k) { emit(M4_PUSH, f.slot, 0, 0); f.i++; f.child_done = false; continue; }
+            used[f.slot] = 0;
+            finished = true;
+        }
+        if (finished) {
+            for (size_t t = first_tip; t < f.tips.size(); t++) { emit(M4_TIP_MUL, 0, f.tips[t], 0); out.tip_order.push_back(f.tips[t]); }
+            if (scaled[f.v]) out.ops[out.ops.size() - 2] |= M4_SCALE_FLAG;
+            if (f.v == root) emit(M4_ROOT, 0, 0, 0);
+            st.pop_back();
+        }
+    }
+    out.nslots = std::max<int>(1, (int)used.size());
     return "";
 }
 

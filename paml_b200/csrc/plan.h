@@ -24,6 +24,29 @@ struct Plan {
     long long n_internal_children = 0, n_tip_children = 0;   // per tree walk (for flop / byte accounting)
 };
 
+// ---- macro-op program of the 4-state register kernel (prune4v2.cuh) ----
+// The 4-state kernel walks a flatter program: one 2-int macro-op per (almost every) internal node, so that the
+// interpretive overhead per FP64 instruction stays below one.  A thread carries ONE running vector `acc`
+// (4 doubles per pattern); parked partial products live in shared-memory slots.
+//   M4_CHERRY   a,b   acc  = PT_a[code] * PT_b[code]                (node whose first two children are tips)
+//   M4_MV_TIP   a,b   acc  = (P_a . acc) * PT_b[code]               (one internal child, then a tip)
+//   M4_MV_PUSH  a,s   slot[s] = P_a . acc                           (first of several internal children: park)
+//   M4_MV_POP   a,s   acc  = (P_a . acc) * slot[s]                  (next internal child joins the parked product)
+//   M4_PUSH     s     slot[s] = acc                                 (park again: more internal children follow)
+//   M4_TIP_MUL  a     acc *= PT_a[code]                             (further tip children)
+//   M4_ROOT           root reduction with pi
+// word 0 = opcode | M4_SCALE_FLAG (NodeScale the finished node) | slot << 8; word 1 = a | b << 16.
+// Tips are consumed in the order of `tip_order`; the kernel reads their codes from a walk-ordered packing.
+enum { M4_CHERRY = 0, M4_MV_TIP = 1, M4_MV_PUSH = 2, M4_MV_POP = 3, M4_PUSH = 4, M4_TIP_MUL = 5, M4_ROOT = 6 };
+enum { M4_SCALE_FLAG = 16 };
+struct Plan4 {
+    std::vector<int> ops;        // 2 ints per macro-op
+    std::vector<int> tip_order;  // tip node ids in consumption order
+    int nslots = 0, nscale = 0;
+};
+std::string plan_tree4(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                       const unsigned char* scale_flags, Plan4& out);
+
 // Returns "" on success, else an error message.
 std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
                       const unsigned char* scale_flags, Plan& out);

@@ -33,6 +33,24 @@ def plan_tree(nnode, ns, root, nson, sons, scale_flags=None):
     return prog, nslots.value
 
 
+def plan_tree4(nnode, ns, root, nson, sons, scale_flags=None):
+    """Planner of the 4-state kernel's macro-op program (no GPU): returns (ops int32 [nops, 2], tip_order, nslots)."""
+    L = lib()
+    nson = np.ascontiguousarray(nson, np.int32)
+    sons = np.ascontiguousarray(sons, np.int32)
+    maxsons = sons.shape[1]
+    flags = None if scale_flags is None else np.ascontiguousarray(scale_flags, np.uint8)
+    nslots, ntip = C.c_int(0), C.c_int(0)
+    args = (C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int), C.c_int(maxsons), _ptr(flags, C.c_ubyte))
+    need = L.pb200_plan_tree4(*args, None, C.c_int(0), None, C.c_int(0), C.byref(ntip), C.byref(nslots))
+    if need < 0:
+        raise PB200Error(L.pb200_last_error().decode())
+    ops = np.zeros(need, np.int32)
+    tips = np.zeros(ntip.value, np.int32)
+    L.pb200_plan_tree4(*args, _ptr(ops, C.c_int), C.c_int(need), _ptr(tips, C.c_int), C.c_int(ntip.value), C.byref(ntip), C.byref(nslots))
+    return ops.reshape(-1, 2), tips, nslots.value
+
+
 def default_scale_flags(nnode, root, nson, sons, every):
     nson = np.ascontiguousarray(nson, np.int32)
     sons = np.ascontiguousarray(sons, np.int32)

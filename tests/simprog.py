@@ -73,3 +73,81 @@ def run_program(prog, nslots, p, pmat_fn):
         lnf = np.log(np.maximum((p.freqK[:, None] * fhK).sum(0), 1e-300))
     lnf = np.where(p.fpatt > 0, lnf, 0.0)
     return -(lnf * p.fpatt).sum(), lnf
+
+
+# ---- macro-op program of the 4-state kernel (paml_b200/csrc/plan.h, Plan4) ----
+M4_CHERRY, M4_MV_TIP, M4_MV_PUSH, M4_MV_POP, M4_PUSH, M4_TIP_MUL, M4_ROOT = range(7)
+M4_SCALE_FLAG = 16
+
+
+def run_program4(ops, tip_order, nslots, p, pmat_fn):
+    """Interprets the macro-op stream exactly as prune4v2_kernel does (one running vector, parked partial products,
+    tips consumed in tip_order).  Returns (neg_lnL, lnf)."""
+    n, N, K = p.n, p.npatt, p.nclass
+    nscale = int(p.scale_flags.sum()) if p.scale_flags is not None else 0
+    fhK = np.zeros((K, N))
+
+    def tip_rows(cls, node, ti):
+        assert tip_order[ti] == node, "tip consumed out of order"
+        P = pmat_fn(cls, node)
+        zs = p.z[node]
+        contrib = np.zeros((N, n))
+        for code in np.unique(zs):
+            states = p.charamap[code, :p.nchara[code]]
+            contrib[zs == code] = P[:, states].sum(1)
+        return contrib
+
+    for cls in range(K):
+        slots = [None] * nslots
+        acc = None
+        lnsc = np.zeros(N)
+        ti = 0
+        done = False
+        for w0, w1 in ops:
+            assert not done, "ops after ROOT"
+            opc, slot = w0 & 15, (w0 >> 8) & 255
+            a, b = w1 & 0xffff, (w1 >> 16) & 0xffff
+            if opc == M4_CHERRY:
+                acc = tip_rows(cls, a, ti) * tip_rows(cls, b, ti + 1); ti += 2
+            elif opc == M4_MV_TIP:
+                acc = (acc @ pmat_fn(cls, a).T) * tip_rows(cls, b, ti); ti += 1
+            elif opc == M4_MV_PUSH:
+                assert slots[slot] is None, "slot overwritten while live"
+                slots[slot] = acc @ pmat_fn(cls, a).T
+                acc = None
+            elif opc == M4_MV_POP:
+                assert slots[slot] is not None, "read of an empty slot"
+                acc = (acc @ pmat_fn(cls, a).T) * slots[slot]
+                slots[slot] = None
+            elif opc == M4_PUSH:
+                assert slots[slot] is None
+                slots[slot] = acc
+                acc = None
+            elif opc == M4_TIP_MUL:
+                acc = acc * tip_rows(cls, a, ti); ti += 1
+            else:
+                assert opc == M4_ROOT
+                fh = acc @ p.pi
+                if p.semantics == 0:
+                    fh = np.where(fh <= 0, 1e-80, fh)
+                    fhK[cls] = np.log(fh) + lnsc
+                else:
+                    fh = np.where(fh <= 0, 1e-300, fh)
+                    fhK[cls] = np.log(fh) + lnsc if nscale else fh
+                done = True
+            if w0 & M4_SCALE_FLAG:
+                mx = acc.max(1)
+                tiny = mx < 1e-300
+                acc[tiny] = 1.0
+                acc[~tiny] /= mx[~tiny, None]
+                lnsc += np.where(tiny, -800.0, np.log(np.where(tiny, 1.0, mx)))
+        assert done and ti == len(tip_order) and all(s is None for s in slots)
+    if p.semantics == 0:
+        lnf = fhK[0]
+    elif nscale:
+        t = fhK.max(0)
+        lnf = t + np.log((p.freqK[:, None] * np.exp(fhK - t)).sum(0))
+    else:
+        lnf = np.log(np.maximum((p.freqK[:, None] * fhK).sum(0), 1e-300))
+    lnf = np.where(p.fpatt > 0, lnf, 0.0)
+    return -(lnf * p.fpatt).sum(), lnf

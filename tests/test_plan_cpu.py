@@ -6,7 +6,7 @@ from conftest import GOLDEN, golden_ids
 from paml_b200.fixture import load_fixture
 from paml_b200 import likelihood, simulate
 from oracle import oracle
-from simprog import run_program
+from simprog import run_program, run_program4
 
 
 def _pmat_fn(p):
@@ -45,6 +45,55 @@ def test_program_on_synthetic_trees(shape, ns):
     r = oracle.lnl(p)
     v, lnf = run_program(prog, nslots, p, _pmat_fn(p))
     assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
+
+
+@pytest.mark.parametrize("path", [g for g in GOLDEN if "brown" in g], ids=[i for i in golden_ids() if "brown" in i])
+def test_program4_reproduces_reference(path):
+    # the 4-state kernel's macro-op program on the nucleotide fixtures (incl. ambiguity codes and the clock tree)
+    p = load_fixture(path)
+    ops, tips, nslots = likelihood.plan_tree4(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags)
+    v, lnf = run_program4(ops, tips, nslots, p, _pmat_fn(p))
+    assert abs(v - p.ref_neg_lnL) <= 1e-10 * abs(p.ref_neg_lnL)
+    np.testing.assert_allclose(lnf, p.ref_lnf, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape,ns", [("random", 40), ("balanced", 64), ("caterpillar", 30), ("random", 5), ("random", 150)])
+def test_program4_on_synthetic_trees(shape, ns):
+    from paml_b200.tree import random_tree
+    p = simulate.nuc_gtr_gamma_problem(ns=ns, npatt=200, seed=21 + ns, K=2)
+    t = random_tree(ns, 9 + ns, shape=shape)
+    p.father, p.nson, p.sons, p.root, p.nnode, p.maxsons = t.father, t.nson, t.sons, t.root, t.nnode, t.maxsons
+    p.branch_t = np.array([0.4, 1.7])[:, None] * t.branch[None, :]
+    p.branch_set = np.zeros((2, t.nnode), np.int32)
+    p.nscale, p.scale_flags = likelihood.default_scale_flags(t.nnode, t.root, t.nson, t.sons, 7)
+    ops, tips, nslots = likelihood.plan_tree4(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags)
+    assert sorted(tips.tolist()) == list(range(ns))
+    assert nslots <= max(1, int(np.ceil(np.log2(ns))))
+    if shape == "caterpillar":
+        assert nslots <= 1
+    # one macro-op per internal node, plus the parks, plus extra tips of multifurcations, plus ROOT
+    assert len(ops) <= 2 * (t.nnode - ns) + 2
+    r = oracle.lnl(p)
+    v, lnf = run_program4(ops, tips, nslots, p, _pmat_fn(p))
+    assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
+
+
+def test_program4_multifurcations():
+    from paml_b200.tree import parse_newick
+    for nwk in ["((1:.1,2:.1):.1,(3:.1,4:.1):.1,(5:.1,6:.1):.1,(7:.1,8:.1):.1,(9:.1,10:.1):.1,11:.2);",
+                "(1:.1,2:.2,3:.3,4:.1,(5:.2,6:.1,7:.3):.2);", "(1:.1,2:.2);", "((1:.1,2:.2):.1,3:.2,(4:.1,(5:.1,6:.2):.1):.3,7:.1);"]:
+        t = parse_newick(nwk)
+        p = simulate.nuc_gtr_gamma_problem(ns=max(t.ns, 4), npatt=120, seed=5, K=2)
+        p.z, p.ns = p.z[:t.ns], t.ns
+        p.father, p.nson, p.sons, p.root, p.nnode, p.maxsons = t.father, t.nson, t.sons, t.root, t.nnode, t.maxsons
+        p.branch_t = np.array([0.4, 1.7])[:, None] * t.branch[None, :]
+        p.branch_set = np.zeros((2, t.nnode), np.int32)
+        p.nscale, p.scale_flags = 0, np.zeros(t.nnode, np.uint8)
+        ops, tips, nslots = likelihood.plan_tree4(p.nnode, p.ns, p.root, p.nson, p.sons, None)
+        assert nslots == 1
+        r = oracle.lnl(p)
+        v, lnf = run_program4(ops, tips, nslots, p, _pmat_fn(p))
+        assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
 
 
 def test_multifurcation_is_folded():
