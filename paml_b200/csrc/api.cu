@@ -694,6 +694,9 @@ static int launch_prune4v2(pb200_ctx* c, int nclass, int semantics, const double
     if (v == 41) return launch_prune4v2_t<4, 256, 1>(c, nclass, semantics, d_pi);
     if (v == 21) return launch_prune4v2_t<2, 128, 4>(c, nclass, semantics, d_pi);
     if (v == 3) return launch_prune4v2_t<3, 128, 3>(c, nclass, semantics, d_pi);
+    if (v == 23) return launch_prune4v2_t<2, 384, 2>(c, nclass, semantics, d_pi);
+    if (v == 27) return launch_prune4v2_t<2, 768, 1>(c, nclass, semantics, d_pi);
+    if (v == 13) return launch_prune4v2_t<1, 512, 2>(c, nclass, semantics, d_pi);
     return launch_prune4v2_t<2, 256, 2>(c, nclass, semantics, d_pi);
 }
 

@@ -202,8 +202,20 @@ std::string plan_tree4(int nnode, int ns, int root, const int* nson, const int* 
     std::vector<char> used;
     auto alloc = [&]() { for (size_t i = 0; i < used.size(); i++) if (!used[i]) { used[i] = 1; return (int)i; }
                          used.push_back(1); return (int)used.size() - 1; };
+    const int ntip_total = ns, ngroups = (ntip_total + 3) / 4;
+    auto tip_field = [&](int ti) {          // where tip number ti of the walk sits in the packed code words
+        const int g = ti >> 2, byte = ti & 3;
+        int adv = 0;
+        if (byte == 0 && g > 0) adv = (g + 4 < ngroups) ? 1 : 2;
+        return byte | (adv << 2) | ((g & 3) << 4);
+    };
     auto emit = [&](int opc, int slot, int a, int b) {
-        out.ops.push_back(opc | (slot << 8));
+        int ntips = (opc == M4_CHERRY) ? 2 : (opc == M4_MV_TIP || opc == M4_TIP_MUL) ? 1 : 0;
+        int ti = (int)out.tip_order.size();            // tips are pushed to tip_order right after their op is emitted
+        int w0 = opc | (slot << M4_SLOT_SHIFT);
+        if (ntips >= 1) w0 |= tip_field(ti) << M4_TIPF0_SHIFT;
+        if (ntips >= 2) w0 |= tip_field(ti + 1) << M4_TIPF1_SHIFT;
+        out.ops.push_back(w0);
         out.ops.push_back((a & 0xffff) | (b << 16));
     };
     struct Frame { int v; std::vector<int> ic, tips; size_t i; int slot; bool child_done; };

@@ -35,10 +35,14 @@ struct Plan {
 //   M4_PUSH     s     slot[s] = acc                                 (park again: more internal children follow)
 //   M4_TIP_MUL  a     acc *= PT_a[code]                             (further tip children)
 //   M4_ROOT           root reduction with pi
-// word 0 = opcode | M4_SCALE_FLAG (NodeScale the finished node) | slot << 8; word 1 = a | b << 16.
-// Tips are consumed in the order of `tip_order`; the kernel reads their codes from a walk-ordered packing.
+// word 0 = opcode [0:3] | M4_SCALE_FLAG (NodeScale the finished node) | tip field 0 << 5 | tip field 1 << 11 |
+// slot << 17; word 1 = a | b << 16.  Tips are consumed in the order of `tip_order`; the kernel reads their codes
+// from a walk-ordered packing, 4 codes per 32-bit word, and everything about WHERE a tip's code sits is static, so
+// it travels in the op: tip field = byte in the word [0:1] | advance [2:3] (0 stay in the current word, 1 move to
+// the next word and prefetch the word four ahead of it, 2 move only) | word index mod 4 [4:5].  Field 0 belongs to the
+// first tip an op consumes, field 1 to the second (M4_CHERRY).
 enum { M4_CHERRY = 0, M4_MV_TIP = 1, M4_MV_PUSH = 2, M4_MV_POP = 3, M4_PUSH = 4, M4_TIP_MUL = 5, M4_ROOT = 6 };
-enum { M4_SCALE_FLAG = 16 };
+enum { M4_SCALE_FLAG = 16, M4_TIPF0_SHIFT = 5, M4_TIPF1_SHIFT = 11, M4_SLOT_SHIFT = 17 };
 struct Plan4 {
     std::vector<int> ops;        // 2 ints per macro-op
     std::vector<int> tip_order;  // tip node ids in consumption order

@@ -10,7 +10,8 @@
 // ambiguity sums pre-added by pt_kernel) are staged once per block in shared memory and read as warp broadcasts /
 // per-code gathers.  Tip codes come from a WALK-ORDERED packing of com.z built once per (data, tree): word g of
 // pattern h holds the codes of tips 4g..4g+3 in the order the program consumes them, so a thread streams its
-// codes with coalesced 32-bit loads issued DEPTH words ahead and extracts them with one byte-permute per tip.
+// codes with coalesced 32-bit loads issued four words (16 tips) ahead and extracts them with one byte-permute per tip;
+// where each tip's code sits is static, so it is encoded in the op (no run-time bookkeeping).
 // Conditional vectors never touch HBM: per class the kernel reads 1 byte per tip and pattern and writes one double.
 #pragma once
 #include "kernels.cuh"
@@ -48,33 +49,58 @@ __global__ void pack_tips4_kernel(const unsigned char* __restrict__ z, long long
     }
 }
 
+__device__ __forceinline__ double2 lds_f64x2(unsigned int addr)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2_volatile(unsigned int addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64x2(unsigned int addr, double a, double b)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(a), "d"(b) : "memory");
+}
+
 template <int PPT, int THREADS, int MINB, bool PSM, bool CP>
 __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2Params p)
 {
     extern __shared__ __align__(16) double sm4v2[];
-    constexpr int DEPTH = 3;                        // code words in flight ahead of the one being consumed
     const int tid = threadIdx.x;
     const int cls = blockIdx.y;
     const long long N = p.npatt;
     const int pstride = p.pstride;
-    double* Psm = sm4v2;                                                              // [nnode][pstride] (if PSM)
-    double2* slots = reinterpret_cast<double2*>(sm4v2 + (PSM ? (size_t)p.nnode * pstride : 0));   // [nslots][PPT][2][THREADS]
+    const unsigned int pstride_b = (unsigned int)pstride * 8u;
     const double* Pg = p.P + (size_t)cls * p.nnode * pstride;
     if (PSM) {
         const double2* src = reinterpret_cast<const double2*>(Pg);
-        double2* dst = reinterpret_cast<double2*>(Psm);
+        double2* dst = reinterpret_cast<double2*>(sm4v2);
         for (int e = tid; e < p.nnode * pstride / 2; e += THREADS) dst[e] = src[e];
         __syncthreads();
     }
-    const double* Pbase = PSM ? Psm : Pg;
+    // shared-memory byte addresses: the class's matrices [nnode][pstride] (if PSM), then the parked slots
+    // [nslots][PPT][2][THREADS] x 16 bytes
+    const unsigned int smem0 = (unsigned int)__cvta_generic_to_shared(sm4v2);
+    const unsigned int slot0 = smem0 + (PSM ? (unsigned int)p.nnode * pstride_b : 0u) + (unsigned int)tid * 16u;
+    constexpr unsigned int SLOT_BYTES = PPT * 2 * THREADS * 16;
     const double pi0 = p.pi[0], pi1 = p.pi[1], pi2 = p.pi[2], pi3 = p.pi[3];
     const int nops = p.nops, ngroups = p.ngroups;
-    double2* myslot = slots + tid;
+    const size_t zws = (size_t)p.zwstride;
+
+    // 16 bytes of matrix `node` of this class at byte offset `off` (a warp-wide broadcast or a per-code gather)
+    auto ldP = [&](unsigned int node_off, unsigned int off) -> double2 {
+        if (PSM) return lds_f64x2(smem0 + node_off + off);
+        return __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const char*>(Pg) + node_off + off));
+    };
 
     for (long long base = (long long)blockIdx.x * THREADS * PPT; base < N; base += (long long)gridDim.x * THREADS * PPT) {
         long long h[PPT];
         const unsigned int* zp[PPT];
-        unsigned int cw[PPT], nw[PPT][DEPTH];
+        unsigned int cw[PPT], r[PPT][4];                 // current code word; ring of the next four (word g lives in r[g & 3])
 #pragma unroll
         for (int u = 0; u < PPT; u++) {
             h[u] = base + (long long)u * THREADS + tid;
@@ -82,39 +108,39 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             zp[u] = p.zw + hc;
             cw[u] = __ldg(zp[u]);
 #pragma unroll
-            for (int d = 0; d < DEPTH; d++) nw[u][d] = (d + 1 < ngroups) ? __ldg(zp[u] + (size_t)(d + 1) * p.zwstride) : 0u;
-            zp[u] += (size_t)(DEPTH + 1) * p.zwstride;           // next word to fetch
+            for (int d = 1; d <= 4; d++) r[u][d & 3] = (d < ngroups) ? __ldg(zp[u] + (size_t)d * zws) : 0u;
+            zp[u] += 5 * zws;                                   // next word to fetch
         }
-        int ti = 0;
         double acc[PPT][4], lnsc[PPT];
 #pragma unroll
         for (int u = 0; u < PPT; u++) { lnsc[u] = 0.0; acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 1.0; }
 
-        // next tip code of every pattern of this thread (offset of its PT row in doubles = 4*code)
-        auto take = [&](int (&off)[PPT]) {
-            const unsigned int sel = 0x4440u | (unsigned int)(ti & 3);
-#pragma unroll
-            for (int u = 0; u < PPT; u++) off[u] = (int)__byte_perm(cw[u], 0u, sel) * 4;
-            ti++;
-            if ((ti & 3) == 0) {
-                const bool more = (ti >> 2) + DEPTH < ngroups;
+        // byte offset of the PT row of the next tip, for every pattern of this thread; `f` is the op's static tip field
+        auto take = [&](int f, unsigned int (&off)[PPT]) {
+            const int adv = (f >> 2) & 3;
+            if (adv) {
+                const int k = (f >> 4) & 3;
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
-                    cw[u] = nw[u][0];
-#pragma unroll
-                    for (int d = 0; d + 1 < DEPTH; d++) nw[u][d] = nw[u][d + 1];
-                    if (more) { nw[u][DEPTH - 1] = __ldg(zp[u]); zp[u] += p.zwstride; }
+                    const unsigned int* src = zp[u];
+                    if (k == 0)      { cw[u] = r[u][0]; if (adv == 1) r[u][0] = __ldg(src); }
+                    else if (k == 1) { cw[u] = r[u][1]; if (adv == 1) r[u][1] = __ldg(src); }
+                    else if (k == 2) { cw[u] = r[u][2]; if (adv == 1) r[u][2] = __ldg(src); }
+                    else             { cw[u] = r[u][3]; if (adv == 1) r[u][3] = __ldg(src); }
+                    zp[u] += zws;
                 }
             }
+            const unsigned int sel = 0x4440u | (unsigned int)(f & 3);
+#pragma unroll
+            for (int u = 0; u < PPT; u++) off[u] = __byte_perm(cw[u], 0u, sel) * 32u;
         };
-        auto row = [&](const double* Pm, int off, double (&c)[4]) {
-            const double2 a = *reinterpret_cast<const double2*>(Pm + off);
-            const double2 b = *reinterpret_cast<const double2*>(Pm + off + 2);
+        auto row = [&](unsigned int node_off, unsigned int off, double (&c)[4]) {
+            const double2 a = ldP(node_off, off), b = ldP(node_off, off + 16u);
             c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
         };
-        auto load16 = [&](const double* Pm, double (&Pr)[16]) {
+        auto load16 = [&](unsigned int node_off, double (&Pr)[16]) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) { const double2 t = *reinterpret_cast<const double2*>(Pm + e); Pr[e] = t.x; Pr[e + 1] = t.y; }
+            for (int e = 0; e < 16; e += 2) { const double2 t = ldP(node_off, 8u * e); Pr[e] = t.x; Pr[e + 1] = t.y; }
         };
         auto matvec = [&](const double (&Pr)[16], const double (&v)[4], double (&t)[4]) {
 #pragma unroll
@@ -125,24 +151,28 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
                 t[j] = fma(Pr[j * 4 + 3], v[3], s);
             }
         };
-
-        for (int op = 0; op < nops; op++) {
-            int w0, w1;
+        auto op_words = [&](int op, int& w0, int& w1) {
             if (CP) { w0 = c_prog[2 * op]; w1 = c_prog[2 * op + 1]; }
             else { const int2 w = __ldg(reinterpret_cast<const int2*>(p.ops) + op); w0 = w.x; w1 = w.y; }
+        };
+
+        int nw0, nw1;
+        op_words(0, nw0, nw1);
+        for (int op = 0; op < nops; op++) {
+            const int w0 = nw0, w1 = nw1;
+            op_words(op + 1 < nops ? op + 1 : op, nw0, nw1);            // the next op's words are in flight during this op
             const int opc = w0 & 15;
-            const int a = w1 & 0xffff, b = (w1 >> 16) & 0xffff;
-            double2* sl = myslot + (size_t)((w0 >> 8) & 255) * (PPT * 2 * THREADS);
+            const unsigned int a_off = (unsigned int)(w1 & 0xffff) * pstride_b, b_off = ((unsigned int)w1 >> 16) * pstride_b;
+            const unsigned int sl = slot0 + (((unsigned int)w0 >> M4_SLOT_SHIFT) & 255u) * SLOT_BYTES;
             switch (opc) {
             case M4_CHERRY: {
                 // two tip children (src/baseml.c:1547-1558): rows of PT[code][j] = sum of the columns of P the code allows
-                int oa[PPT], ob[PPT];
-                take(oa); take(ob);
-                const double *Pa = Pbase + (size_t)a * pstride, *Pb = Pbase + (size_t)b * pstride;
+                unsigned int oa[PPT], ob[PPT];
+                take(w0 >> M4_TIPF0_SHIFT, oa); take(w0 >> M4_TIPF1_SHIFT, ob);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double ra[4], rb[4];
-                    row(Pa, oa[u], ra); row(Pb, ob[u], rb);
+                    row(a_off, oa[u], ra); row(b_off, ob[u], rb);
 #pragma unroll
                     for (int j = 0; j < 4; j++) acc[u][j] = ra[j] * rb[j];
                 }
@@ -151,14 +181,13 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             case M4_MV_TIP: {
                 // internal child still in registers (src/baseml.c:1559-1566), then a tip child
                 double Pr[16];
-                load16(Pbase + (size_t)a * pstride, Pr);
-                int ob[PPT];
-                take(ob);
-                const double* Pb = Pbase + (size_t)b * pstride;
+                load16(a_off, Pr);
+                unsigned int ob[PPT];
+                take(w0 >> M4_TIPF0_SHIFT, ob);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double t[4], rb[4];
-                    row(Pb, ob[u], rb);
+                    row(b_off, ob[u], rb);
                     matvec(Pr, acc[u], t);
 #pragma unroll
                     for (int j = 0; j < 4; j++) acc[u][j] = t[j] * rb[j];
@@ -167,23 +196,23 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             }
             case M4_MV_PUSH: {
                 double Pr[16];
-                load16(Pbase + (size_t)a * pstride, Pr);
+                load16(a_off, Pr);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double t[4];
                     matvec(Pr, acc[u], t);
-                    sl[(u * 2 + 0) * THREADS] = make_double2(t[0], t[1]);
-                    sl[(u * 2 + 1) * THREADS] = make_double2(t[2], t[3]);
+                    sts_f64x2(sl + (u * 2 + 0) * THREADS * 16, t[0], t[1]);
+                    sts_f64x2(sl + (u * 2 + 1) * THREADS * 16, t[2], t[3]);
                 }
                 break;
             }
             case M4_MV_POP: {
                 double Pr[16];
-                load16(Pbase + (size_t)a * pstride, Pr);
+                load16(a_off, Pr);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double t[4];
-                    const double2 s0 = sl[(u * 2 + 0) * THREADS], s1 = sl[(u * 2 + 1) * THREADS];
+                    const double2 s0 = lds_f64x2_volatile(sl + (u * 2 + 0) * THREADS * 16), s1 = lds_f64x2_volatile(sl + (u * 2 + 1) * THREADS * 16);
                     matvec(Pr, acc[u], t);
                     acc[u][0] = t[0] * s0.x; acc[u][1] = t[1] * s0.y; acc[u][2] = t[2] * s1.x; acc[u][3] = t[3] * s1.y;
                 }
@@ -192,19 +221,18 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             case M4_PUSH: {
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
-                    sl[(u * 2 + 0) * THREADS] = make_double2(acc[u][0], acc[u][1]);
-                    sl[(u * 2 + 1) * THREADS] = make_double2(acc[u][2], acc[u][3]);
+                    sts_f64x2(sl + (u * 2 + 0) * THREADS * 16, acc[u][0], acc[u][1]);
+                    sts_f64x2(sl + (u * 2 + 1) * THREADS * 16, acc[u][2], acc[u][3]);
                 }
                 break;
             }
             case M4_TIP_MUL: {
-                int oa[PPT];
-                take(oa);
-                const double* Pa = Pbase + (size_t)a * pstride;
+                unsigned int oa[PPT];
+                take(w0 >> M4_TIPF0_SHIFT, oa);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double ra[4];
-                    row(Pa, oa[u], ra);
+                    row(a_off, oa[u], ra);
 #pragma unroll
                     for (int j = 0; j < 4; j++) acc[u][j] *= ra[j];
                 }

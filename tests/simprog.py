@@ -87,8 +87,13 @@ def run_program4(ops, tip_order, nslots, p, pmat_fn):
     nscale = int(p.scale_flags.sum()) if p.scale_flags is not None else 0
     fhK = np.zeros((K, N))
 
-    def tip_rows(cls, node, ti):
+    ngroups = (len(tip_order) + 3) // 4
+
+    def tip_rows(cls, node, ti, field):
         assert tip_order[ti] == node, "tip consumed out of order"
+        g, byte = ti >> 2, ti & 3                  # the static placement the kernel relies on
+        adv = 0 if (byte != 0 or g == 0) else (1 if g + 4 < ngroups else 2)
+        assert field == (byte | (adv << 2) | ((g & 3) << 4)), "bad tip field"
         P = pmat_fn(cls, node)
         zs = p.z[node]
         contrib = np.zeros((N, n))
@@ -105,12 +110,12 @@ def run_program4(ops, tip_order, nslots, p, pmat_fn):
         done = False
         for w0, w1 in ops:
             assert not done, "ops after ROOT"
-            opc, slot = w0 & 15, (w0 >> 8) & 255
+            opc, slot = w0 & 15, (w0 >> 17) & 255
             a, b = w1 & 0xffff, (w1 >> 16) & 0xffff
             if opc == M4_CHERRY:
-                acc = tip_rows(cls, a, ti) * tip_rows(cls, b, ti + 1); ti += 2
+                acc = tip_rows(cls, a, ti, (w0 >> 5) & 63) * tip_rows(cls, b, ti + 1, (w0 >> 11) & 63); ti += 2
             elif opc == M4_MV_TIP:
-                acc = (acc @ pmat_fn(cls, a).T) * tip_rows(cls, b, ti); ti += 1
+                acc = (acc @ pmat_fn(cls, a).T) * tip_rows(cls, b, ti, (w0 >> 5) & 63); ti += 1
             elif opc == M4_MV_PUSH:
                 assert slots[slot] is None, "slot overwritten while live"
                 slots[slot] = acc @ pmat_fn(cls, a).T
@@ -124,7 +129,7 @@ def run_program4(ops, tip_order, nslots, p, pmat_fn):
                 slots[slot] = acc
                 acc = None
             elif opc == M4_TIP_MUL:
-                acc = acc * tip_rows(cls, a, ti); ti += 1
+                acc = acc * tip_rows(cls, a, ti, (w0 >> 5) & 63); ti += 1
             else:
                 assert opc == M4_ROOT
                 fh = acc @ p.pi
