@@ -26,8 +26,10 @@ typedef struct pb200_ctx pb200_ctx;
  *   PB200_KIND_UVROOT   Root[n], U[n*n], V[n*n] (row-major)   PMatUVRoot, src/tools.c:516-546
  *   PB200_KIND_CIJK     Root[nr], Cijk[n*n*nr]                PMatCijk,   src/baseml.c:1572-1589
  *   PB200_KIND_K80      kappa                                 PMatK80,    src/tools.c:578-606
- *   PB200_KIND_JC69LIKE (nothing)                             PMatJC69like, src/codeml.c:3585-3594       */
-enum { PB200_KIND_UVROOT = 0, PB200_KIND_CIJK = 1, PB200_KIND_K80 = 2, PB200_KIND_JC69LIKE = 3 };
+ *   PB200_KIND_JC69LIKE (nothing)                             PMatJC69like, src/codeml.c:3585-3594
+ *   PB200_KIND_QMATEXP  Q[n*n] (row-major rate matrix, n<=16) matexp(Q t, 7, 5), src/treesub.c:7523-7527,
+ *                                                             src/tools.c:4879-4919 (UNREST / UNRESTu)   */
+enum { PB200_KIND_UVROOT = 0, PB200_KIND_CIJK = 1, PB200_KIND_K80 = 2, PB200_KIND_JC69LIKE = 3, PB200_KIND_QMATEXP = 4 };
 
 /* Which reference function's arithmetic pb200_eval reproduces:
  *   PB200_SEM_LFUN    lfun   (src/treesub.c:7764-7807): one class, f_h <= 0 -> 1e-80

@@ -75,9 +75,38 @@ void orc_pmat_jc69like(double *P, double t, int n)
    for (i = 0; i < n; i++) P[i * n + i] = pii;
 }
 
+/* treesub.c:7523-7527 (UNREST branch of baseml's GetPMatBranch): P = matexp(Q t) with 7 Taylor terms and 5
+   squarings, tools.c:4879-4919: B = Qt/2^5; S = I + B + B^2/2! + ... + B^7/7!; P = S^(2^5).
+   No clamping of negative entries and no small-t shortcut on this path. */
+void orc_pmat_qmatexp(double *P, double t, int n, const double *Q)
+{
+   enum { NTAYLOR = 7, NSQUARE = 5 };
+   double B[64 * 64], S[64 * 64], pw[64 * 64], nx[64 * 64], factor = 1, s;
+   int i, j, k, term, sq, nn = n * n;
+   for (i = 0; i < nn; i++) { B[i] = Q[i] * t * (1.0 / (1 << NSQUARE)); S[i] = B[i]; pw[i] = B[i]; }
+   for (i = 0; i < n; i++) S[i * n + i] += 1;
+   for (term = 2; term <= NTAYLOR; term++) {
+      for (i = 0; i < n; i++) for (j = 0; j < n; j++) {
+         for (k = 0, s = 0; k < n; k++) s += pw[i * n + k] * B[k * n + j];
+         nx[i * n + j] = s;
+      }
+      factor /= term;
+      for (i = 0; i < nn; i++) { pw[i] = nx[i]; S[i] += nx[i] * factor; }
+   }
+   for (sq = 0; sq < NSQUARE; sq++) {
+      for (i = 0; i < n; i++) for (j = 0; j < n; j++) {
+         for (k = 0, s = 0; k < n; k++) s += S[i * n + k] * S[k * n + j];
+         nx[i * n + j] = s;
+      }
+      for (i = 0; i < nn; i++) S[i] = nx[i];
+   }
+   for (i = 0; i < nn; i++) P[i] = S[i];
+}
+
 void orc_pmat(double *P, double t, int n, int kind, int nr, const double *set)
 {
    switch (kind) {
+   case ORC_KIND_QMATEXP:  orc_pmat_qmatexp(P, t, n, set); break;
    case ORC_KIND_UVROOT:   orc_pmat_uvroot(P, t, n, set + n, set + n + (size_t)n * n, set); break;
    case ORC_KIND_CIJK:     orc_pmat_cijk(P, t, n, nr, set + nr, set); break;
    case ORC_KIND_K80:      orc_pmat_k80(P, t, set[0]); break;

@@ -12,7 +12,7 @@
 extern "C" {
 #endif
 
-enum { ORC_KIND_UVROOT = 0, ORC_KIND_CIJK = 1, ORC_KIND_K80 = 2, ORC_KIND_JC69LIKE = 3 };
+enum { ORC_KIND_UVROOT = 0, ORC_KIND_CIJK = 1, ORC_KIND_K80 = 2, ORC_KIND_JC69LIKE = 3, ORC_KIND_QMATEXP = 4 };
 enum { ORC_SEM_LFUN = 0, ORC_SEM_LFUNDG = 1 };
 
 /* P(t) routines.  P is row-major n x n, P[i*n+j] = Pr(i -> j | t). */
@@ -20,6 +20,7 @@ void orc_pmat_uvroot(double *P, double t, int n, const double *U, const double *
 void orc_pmat_cijk(double *P, double t, int n, int nr, const double *Cijk, const double *Root);
 void orc_pmat_k80(double *P, double t, double kappa);
 void orc_pmat_jc69like(double *P, double t, int n);
+void orc_pmat_qmatexp(double *P, double t, int n, const double *Q);   /* set = Q[n*n] (UNREST) */
 /* dispatch on kind; set = one spectral set laid out as in the fixtures/C-ABI (see include/paml_b200.h) */
 void orc_pmat(double *P, double t, int n, int kind, int nr, const double *set);
 

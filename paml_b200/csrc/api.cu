@@ -709,7 +709,8 @@ static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride
     p.kind = kind; p.nr = nr; p.set_stride = set_stride; p.sets = d_sets; p.mat_set = d_mat_set; p.mat_t = d_mat_t;
     p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
     p.out = d_out; p.pstride = pstride; p.mode = mode;
-    size_t smem = (kind == KIND_UVROOT ? ((size_t)p.ld * p.ld + 17 * (size_t)p.ld) : 16 * (size_t)p.ld) * sizeof(double);
+    size_t smem = (kind == KIND_UVROOT ? ((size_t)p.ld * p.ld + 17 * (size_t)p.ld)
+                   : kind == KIND_QMATEXP ? (16 * (size_t)p.ld + 3 * (size_t)p.ld * p.ld) : 16 * (size_t)p.ld) * sizeof(double);
     dim3 grid(nmat, (p.ld + 15) / 16);
     pt_kernel<<<grid, 256, smem, c->stream>>>(p);
     c->launches++;
@@ -733,6 +734,10 @@ static int check_sets(int n, int set_kind, int nr, int nset, long long set_strid
         need = 1;
         break;
     case KIND_JC69LIKE: need = 0; break;
+    case KIND_QMATEXP:
+        if (n > 16) return fail("QMATEXP sets need n <= 16");
+        need = (long long)n * n;
+        break;
     default: return fail("unknown set_kind %d", set_kind);
     }
     if (set_stride < need) return fail("set_stride %lld too small for kind %d (need %lld)", set_stride, set_kind, need);

@@ -2,7 +2,8 @@
 //
 //   pt_kernel      batched P(t) for every (site class, branch): replaces PMatUVRoot (src/tools.c:516-546),
 //                  PMatCijk (src/baseml.c:1572-1589), PMatK80 (src/tools.c:578-606), PMatJC69like
-//                  (src/codeml.c:3585-3594) as selected by GetPMatBranch (src/treesub.c:7503-7592).
+//                  (src/codeml.c:3585-3594) and the Taylor + squaring matexp of the UNREST models (src/tools.c:4879-4919)
+//                  as selected by GetPMatBranch (src/treesub.c:7503-7592).
 //   prune_kernel   Felsenstein pruning of whole trees, replaces ConditionalPNode (src/codeml.c:3526-3582,
 //                  src/baseml.c:1517-1570) + NodeScale (src/treesub.c:7200-7230) + the root pi-dot of
 //                  lfun / fx_r (src/treesub.c:7780-7798, 7726-7750).
@@ -19,7 +20,7 @@
 
 namespace pb200 {
 
-enum { KIND_UVROOT = 0, KIND_CIJK = 1, KIND_K80 = 2, KIND_JC69LIKE = 3 };
+enum { KIND_UVROOT = 0, KIND_CIJK = 1, KIND_K80 = 2, KIND_JC69LIKE = 3, KIND_QMATEXP = 4 };
 enum { SEM_LFUN = 0, SEM_LFUNDG = 1 };
 enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2, PT_MODE_NUC4 = 3 };
 
@@ -53,7 +54,8 @@ struct PtParams {
 
 // grid = (matrices, row blocks): CTA (m, rb) computes rows [16rb, 16rb+16) of matrix m with 256 threads
 // (thread = one row x four columns) and writes the part of the consumer's layout that those rows feed.
-// Shared memory: ld*ld (V) + 16*ld (scaled U rows) + ld (expm1 terms) doubles for UVROOT, 16*ld otherwise.
+// Shared memory: ld*ld (V) + 16*ld (scaled U rows) + ld (expm1 terms) doubles for UVROOT, 16*ld + 3*ld*ld for
+// QMATEXP, 16*ld otherwise.
 __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
 {
     extern __shared__ __align__(16) double sm[];
@@ -101,6 +103,44 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
                 if (v < 0) v = 0;                           // src/tools.c:536-537
                 Prow[ty * ld + j] = (i < n && j < n) ? v : 0.0;
             }
+        }
+    }
+    else if (p.kind == KIND_QMATEXP) {
+        // UNREST models (src/treesub.c:7523-7527): P = matexp(Q t, 7 Taylor terms, 5 squarings), src/tools.c:4879-4919:
+        // B = Q t / 2^5, S = I + B + B^2/2! + ... + B^7/7!, P = S^(2^5).  One thread per element (n <= 16, one row
+        // block), products and sums in the reference's order and unfused; no clamping on this path.
+        double* B = sm + 16 * ld;        // [n][n]
+        double* S = B + ld * ld;
+        double* pw = S + ld * ld;        // B^(term-1)
+        const int i = tid / n, j = tid - i * n;
+        const bool on = tid < n * n;
+        double sv = 0.0, factor = 1.0;
+        if (on) {
+            const double b = __dmul_rn(__dmul_rn(set[tid], t), 1.0 / 32);
+            B[tid] = b; pw[tid] = b;
+            sv = (i == j) ? __dadd_rn(b, 1.0) : b;
+        }
+        __syncthreads();
+        for (int term = 2; term <= 7; term++) {
+            double s = 0.0;
+            if (on) for (int k = 0; k < n; k++) s = __dadd_rn(s, __dmul_rn(pw[i * n + k], B[k * n + j]));
+            __syncthreads();             // every read of pw done before it is replaced
+            factor /= term;
+            if (on) { pw[tid] = s; sv = __dadd_rn(sv, __dmul_rn(s, factor)); }
+            __syncthreads();
+        }
+        if (on) S[tid] = sv;
+        __syncthreads();
+        for (int sq = 0; sq < 5; sq++) {
+            double s = 0.0;
+            if (on) for (int k = 0; k < n; k++) s = __dadd_rn(s, __dmul_rn(S[i * n + k], S[k * n + j]));
+            __syncthreads();
+            if (on) S[tid] = s;
+            __syncthreads();
+        }
+        for (int e = tid; e < 16 * ld; e += 256) {
+            const int r = e / ld, c = e - r * ld;
+            Prow[e] = (r < n && c < n) ? S[r * n + c] : 0.0;
         }
     }
     else {

@@ -1,11 +1,21 @@
 /* codeml_b200.c -- codeml with its likelihood function on the GPU.
  * The reference program is compiled from where it lies (-I<reference>/src), unmodified and textually included;
- * only the two hot-path entry points are renamed away and re-defined by plfun_b200.inc. */
+ * only the hot-path entry points are renamed away and re-defined by plfun_b200.inc:
+ *   lfun / lfundG   function-like macros rename the reference DEFINITIONS (and direct calls, of which there are none
+ *                   outside lfundG's own file) while the bare names in `com.plfun = lfun` / `== lfun` bind to ours;
+ *   fx_r            is only ever called directly, always as fx_r(x, ..): the macro below pastes on the first
+ *                   argument, so the reference's definition/prototype `fx_r(double x[], int np)` becomes fx_r_ref and
+ *                   every call `fx_r(x, ..)` becomes fx_r_gpu (any other spelling fails to compile, loudly). */
 double lfun(double x[], int np);
 double lfundG(double x[], int np);
+int fx_r_gpu(double x[], int np);
 #define lfun(a, b)   lfun_ref(a, b)
 #define lfundG(a, b) lfundG_ref(a, b)
+#define fx_r(a, b)   PBH_FXR_##a, b)
+#define PBH_FXR_x      fx_r_gpu(x
+#define PBH_FXR_double fx_r_ref(double
 #include "codeml.c"
 #undef lfun
 #undef lfundG
+#undef fx_r
 #include "plfun_b200.inc"

@@ -17,9 +17,10 @@ def _tree_newick(p, branch):
     return rec(p.root) + ";"
 
 
-def write_pattern_files(p, prefix, h1=None):
+def write_pattern_files(p, prefix, h1=None, genes=None):
     """Write <prefix>.phy (pattern format) and <prefix>.tre for Problem p (clean data only).
-    Branch lengths are class 0's t (for a one-class problem: the branch lengths themselves)."""
+    Branch lengths are class 0's t (for a one-class problem: the branch lengths themselves).
+    genes: pattern counts per gene -> option ``PG`` with a ``G ngene n1 n2 ..`` line (src/treesub.c:624-657)."""
     assert p.cleandata, "pattern writer handles resolved states only"
     h1 = p.npatt if h1 is None else min(h1, p.npatt)
     if p.n == 61:
@@ -31,7 +32,11 @@ def write_pattern_files(p, prefix, h1=None):
     else:
         chars = np.array([[c] for c in models.BASES]); width = 1
     with open(prefix + ".phy", "w") as f:
-        f.write("%d %d P\n" % (p.ns, h1 * width))
+        if genes:
+            assert sum(genes) == h1
+            f.write("%d %d PG\nG %d %s\n" % (p.ns, h1 * width, len(genes), " ".join(str(g) for g in genes)))
+        else:
+            f.write("%d %d P\n" % (p.ns, h1 * width))
         for i in range(p.ns):
             f.write("s%d  " % (i + 1))
             f.write("".join("".join(row) for row in chars[p.z[i, :h1]]))
@@ -41,6 +46,28 @@ def write_pattern_files(p, prefix, h1=None):
     with open(prefix + ".tre", "w") as f:
         f.write("%d 1\n%s\n" % (p.ns, _tree_newick(p, p.branch_t[0])))
     return h1
+
+
+def write_sequence_files(p, prefix, seed=1):
+    """Write <prefix>.phy as an ordinary sequential alignment (every pattern repeated fpatt times, the sites shuffled)
+    and <prefix>.tre: the reference then compresses the sites itself (PatternWeight, src/treesub.c:1386-1516)."""
+    assert p.cleandata
+    if p.n == 61:
+        from61, _ = models.sense_codons()
+        chars = np.array(["".join(models.BASES[k] for k in (ic // 16, (ic // 4) % 4, ic % 4)) for ic in from61]); width = 3
+    elif p.n == 20:
+        chars = np.array(list(models.AAS)); width = 1
+    else:
+        chars = np.array(list(models.BASES)); width = 1
+    sites = np.repeat(np.arange(p.npatt), np.asarray(p.fpatt, dtype=np.int64))
+    np.random.default_rng(seed).shuffle(sites)
+    with open(prefix + ".phy", "w") as f:
+        f.write("%d %d\n" % (p.ns, len(sites) * width))
+        for i in range(p.ns):
+            f.write("s%d  %s\n" % (i + 1, "".join(chars[p.z[i, sites]])))
+    with open(prefix + ".tre", "w") as f:
+        f.write("%d 1\n%s\n" % (p.ns, _tree_newick(p, p.branch_t[0])))
+    return len(sites)
 
 
 def write_codeml_ctl(path, seqfile, treefile, seqtype=1, model=0, NSsites=0, kappa=5.0, omega=0.3, extra=None):

@@ -78,6 +78,19 @@ CASES = [
     dict(name="mhc_m2a", prog="codeml", ctl="MHC.Swanson2002MBE/codeml.ctl", files=["MHC.Swanson2002MBE/bigmhc.phy", "MHC.Swanson2002MBE/bigmhc.trees"],
          ov=dict(seqfile="bigmhc.phy", treefile="bigmhc.trees", NSsites=2, method=0, getSE=0, RateAncestor=0, noisy=2),
          lnL=-7231.154540),
+    # model families beyond the BASELINE configurations: matexp (UNREST), spectral sets per branch (nhomo, free-ratio)
+    dict(name="brown_unrest", prog="baseml", ctl="baseml.ctl", files=["brown.nuc", "brown.trees"],
+         ov=dict(seqfile="brown.nuc", treefile="brown.trees", model=8, fix_alpha=1, alpha=0, getSE=0, RateAncestor=0),
+         lnL=None),
+    dict(name="brown_hky_nhomo4", prog="baseml", ctl="baseml.ctl", files=["brown.nuc", "brown.trees"],
+         ov=dict(seqfile="brown.nuc", treefile="brown.trees", model=4, nhomo=4, fix_alpha=1, alpha=0, getSE=0, RateAncestor=0),
+         lnL=None),
+    dict(name="brown_k80_nhomo2_g4", prog="baseml", ctl="baseml.ctl", files=["brown.nuc", "brown.trees"],
+         ov=dict(seqfile="brown.nuc", treefile="brown.trees", model=1, nhomo=2, fix_alpha=0, alpha=0.5, ncatG=4, getSE=0, RateAncestor=0),
+         lnL=None),
+    dict(name="lysozyme_freeratio", prog="codeml", ctl="lysozyme/lysozymeSmall.ctl", files=["lysozyme/lysozymeSmall.nuc", "lysozyme/lysozymeSmall.trees"],
+         ov=dict(seqfile="lysozymeSmall.nuc", treefile="lysozymeSmall.trees", model=1, NSsites=0, CodonFreq=2, getSE=0, RateAncestor=0, noisy=2),
+         lnL=None),
 ]
 
 

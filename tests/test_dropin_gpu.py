@@ -90,16 +90,3 @@ def test_baseml_gtr_gamma_fit(tmp_path):
         out[tag] = dict(lnL=_lnl(str(d / "mlb")), alpha=float(re.search(r"alpha \(gamma, K=\s*4\) =\s*([\d.]+)", txt).group(1)))
     assert abs(out["gpu"]["lnL"] - out["ref"]["lnL"]) <= 1e-6 * abs(out["ref"]["lnL"]), out
     assert abs(out["gpu"]["alpha"] - out["ref"]["alpha"]) < 5e-3, out
-
-
-def test_unsupported_model_fails_loudly(tmp_path):
-    _need(os.path.join(BIN, "baseml_b200"))
-    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=100, seed=3, K=2)
-    d = tmp_path
-    paml_io.write_pattern_files(p, str(d / "s"))
-    with open(d / "run.ctl", "w") as f:
-        f.write("seqfile = s.phy\ntreefile = s.tre\noutfile = mlb\nnoisy = 0\nrunmode = 0\nmodel = 8\nfix_alpha = 1\nalpha = 0\n"
-                "getSE = 0\nRateAncestor = 0\ncleandata = 1\nmethod = 0\n")          # UNREST: matexp per branch
-    r = subprocess.run([os.path.join(BIN, "baseml_b200"), "run.ctl"], cwd=str(d), stdin=subprocess.DEVNULL,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
-    assert r.returncode != 0 and "not implemented on the GPU path" in r.stdout

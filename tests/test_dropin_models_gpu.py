@@ -1,0 +1,184 @@
+"""The drop-in on the model families beyond the BASELINE configurations (SURVEY.md 8a "model coverage" table and
+8f rank 4): several genes / partitions (Mgene = 0, 2, 3, 4, per-gene alpha), nonhomogeneous baseml models (nhomo =
+2..5: spectral sets per branch), UNREST (Taylor + squaring matexp on the device), free-ratio codon model (more omega
+types than the reference's _UU[] holds: eigen-solution per branch), and the consumers of fx_r: auto-discrete-gamma
+(lfunAdG), NEB (lfunNSsites_rate) and the M2a BEB grid.  Each case runs paml_b200/bin/*_b200 next to the unmodified
+reference binary (oracle/_ref) on the same files and compares what they print."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from paml_b200 import paml_io, simulate
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(REPO, "paml_b200", "bin")
+REF = os.path.join(REPO, "oracle", "_ref")
+
+BASEML_CTL = ("seqfile = s.phy\ntreefile = s.tre\noutfile = mlb\nnoisy = 0\nverbose = 0\nrunmode = 0\nMgene = %(Mgene)d\n"
+              "clock = 0\nMalpha = %(Malpha)d\ngetSE = 0\nRateAncestor = 0\nSmall_Diff = 7e-6\ncleandata = 1\nmethod = 0\n"
+              "model = %(model)d\nfix_kappa = 0\nkappa = 2\nfix_alpha = %(fix_alpha)d\nalpha = %(alpha)s\nncatG = %(ncatG)d\n"
+              "nhomo = %(nhomo)d\nfix_blength = 1\n%(more)s")
+
+
+def _baseml_ctl(path, **kw):
+    d = dict(Mgene=0, Malpha=0, model=4, fix_alpha=1, alpha="0", ncatG=1, nhomo=0, more="")
+    d.update(kw)
+    with open(path, "w") as f:
+        f.write(BASEML_CTL % d)
+
+
+def _run(exe, cwd, ok=True):
+    r = subprocess.run([exe, "run.ctl"], cwd=cwd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=900)
+    if ok:
+        assert r.returncode == 0, r.stdout[-2000:]
+    return r
+
+
+def _lnl(path):
+    m = re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(path).read())
+    assert m, "no lnL line in " + path
+    return float(m[-1])
+
+
+def _pair(prog):
+    gpu, ref = os.path.join(BIN, prog + "_b200"), os.path.join(REF, prog)
+    for p in (gpu, ref):
+        if not os.path.exists(p):
+            pytest.skip("prebuilt binary missing: " + p)
+    return (("gpu", gpu), ("ref", ref))
+
+
+def _both(tmp_path, prog, write, outfile):
+    """write(dir) prepares one run directory; returns {tag: (lnL, dir)}."""
+    res = {}
+    for tag, exe in _pair(prog):
+        d = tmp_path / tag
+        d.mkdir()
+        write(str(d))
+        _run(exe, str(d))
+        res[tag] = (_lnl(str(d / outfile)), str(d))
+    return res
+
+
+def _close(res, rel):
+    g, r = res["gpu"][0], res["ref"][0]
+    assert abs(g - r) <= rel * abs(r), (g, r)
+
+
+@pytest.mark.parametrize("mgene,malpha", [(0, 0), (2, 0), (3, 0), (4, 1)])
+def test_baseml_genes(tmp_path, mgene, malpha):
+    """Two partitions (option G): shared kappa/pi with gene rates (Mgene 0), per-gene pi (2), kappa (3), both + per-gene
+    alpha (4, Malpha 1); every gene is evaluated with its own SetPGene parameters (src/treesub.c:7713-7716, 7773-7775)."""
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=200, seed=33, K=4)
+    n = int(p.npatt)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s", genes=[n - n // 3, n // 3])
+        _baseml_ctl(d + "/run.ctl", Mgene=mgene, Malpha=malpha, fix_alpha=0, alpha="0.5", ncatG=4)
+    _close(_both(tmp_path, "baseml", write, "mlb"), 2e-6)
+
+
+@pytest.mark.parametrize("nhomo", [2, 3, 4, 5])
+def test_baseml_nhomo(tmp_path, nhomo):
+    """Nonhomogeneous models: kappa per branch (2), N1 (3), N2 = pi per node (4), labelled pi sets (5):
+    GetPMatBranch re-derives Root/Cijk for every branch (src/treesub.c:7514-7519) -> one spectral set per branch."""
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=150, seed=32, K=1)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        _baseml_ctl(d + "/run.ctl", nhomo=nhomo)
+    _close(_both(tmp_path, "baseml", write, "mlb"), 5e-6)
+
+
+def test_baseml_unrest(tmp_path):
+    """UNREST (model 8): P(t) by the Taylor + squaring matexp on the device (src/treesub.c:7523-7527)."""
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=150, seed=31, K=1)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        _baseml_ctl(d + "/run.ctl", model=8)
+    _close(_both(tmp_path, "baseml", write, "mlb"), 2e-6)
+
+
+def test_baseml_auto_discrete_gamma(tmp_path):
+    """fix_rho = 0: com.plfun = lfunAdG (src/treesub.c:7447-7494), whose per-class values come from fx_r -> the GPU;
+    its hidden-Markov recursion over the site order stays the reference's host C.  Ordinary (non-pattern) alignment."""
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=200, seed=44, K=4)
+
+    def write(d):
+        paml_io.write_sequence_files(p, d + "/s")
+        _baseml_ctl(d + "/run.ctl", fix_alpha=0, alpha="0.5", ncatG=4, more="fix_rho = 0\nrho = 0.2\n")
+    _close(_both(tmp_path, "baseml", write, "mlb"), 2e-6)
+
+
+@pytest.mark.parametrize("mgene", [0, 3])
+def test_codeml_genes(tmp_path, mgene):
+    p = simulate.codon_m0_problem(ns=6, npatt=200, seed=41)
+    n = int(p.npatt)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s", genes=[n - n // 3, n // 3])
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, Mgene=mgene))
+    _close(_both(tmp_path, "codeml", write, "mlc"), 2e-6)
+
+
+def test_codeml_free_ratio_fixed_point(tmp_path):
+    """model = 1 with 13 branches: more omega types than _UU[] holds, the reference solves an eigen-problem per branch
+    inside GetPMatBranch (src/treesub.c:7574-7583); one evaluation at a fixed point, compared digit for digit."""
+    p = simulate.codon_m0_problem(ns=8, npatt=200, seed=43)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", model=1, kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=2))
+        with open(d + "/in.codeml", "w") as f:
+            f.write("-1  2.0 " + " ".join("%.2f" % (0.1 + 0.07 * i) for i in range(13)) + "\n")
+    _close(_both(tmp_path, "codeml", write, "mlc"), 1e-9)
+
+
+def _numbers(path):
+    """Every decimal number of a report, with the number of decimals it was printed with."""
+    out = []
+    for tok in re.findall(r"-?\d+\.\d+", open(path).read()):
+        out.append((float(tok), len(tok.split(".")[1])))
+    return out
+
+
+def test_codeml_m2a_neb_beb_fixed_point(tmp_path):
+    """M2a at a fixed parameter point: lfundG for the lnL, then NEB (lfunNSsites_rate, src/codeml.c:5241) and the BEB grid
+    of 21 omega classes (src/codeml.c:6280) -- both read com.fhK[] as left by fx_r, which the drop-in computes on the
+    GPU.  The posterior tables in `rst` must agree to the printed precision."""
+    p = simulate.codon_sites_problem(ns=7, npatt=150, seed=42)
+
+    def write(d):
+        paml_io.write_sequence_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", NSsites=2, kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=2, ncatG=3))
+        with open(d + "/in.codeml", "w") as f:
+            f.write("-1  2.0  0.5 0.45  0.1 5.0\n")
+    res = _both(tmp_path, "codeml", write, "mlc")
+    _close(res, 1e-9)
+    g, r = _numbers(res["gpu"][1] + "/rst"), _numbers(res["ref"][1] + "/rst")
+    assert len(g) == len(r) and len(r) > 1000, (len(g), len(r))
+    assert "Bayes Empirical Bayes" in open(res["gpu"][1] + "/rst").read()
+    bad = [(a, b) for (a, da), (b, db) in zip(g, r) if abs(a - b) > 2.5 * 10.0 ** (-min(da, db))]
+    assert not bad, bad[:10]
+
+
+def test_too_many_genes_fails_loudly(tmp_path):
+    """No CPU fallback: what the GPU path does not implement stops the program with a message naming it."""
+    exe = os.path.join(BIN, "baseml_b200")
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt binary missing: " + exe)
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=200, seed=33, K=1)
+    n = int(p.npatt)
+    assert n > 64
+    paml_io.write_pattern_files(p, str(tmp_path / "s"), genes=[1] * n)
+    _baseml_ctl(str(tmp_path / "run.ctl"))
+    r = _run(exe, str(tmp_path), ok=False)
+    assert r.returncode != 0 and "not implemented on the GPU path" in r.stdout, r.stdout[-500:]
