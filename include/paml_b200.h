@@ -103,6 +103,21 @@ int pb200_get_fhK(pb200_ctx *ctx, double *fhK);
 int pb200_pmat(pb200_ctx *ctx, int n, int set_kind, int nr, int nset, long long set_stride,
                const double *set_data, int nmat, const int *mat_set, const double *mat_t, double *P_out);
 
+/* Replaces PatternWeight (src/treesub.c:1386-1516), the step that turns an alignment into the site patterns the
+ * likelihood path consumes: the ls columns are collapsed, gene by gene, into their distinct patterns in ascending
+ * strcmp order of (character + 1), each represented by the first site showing it -- the reference's order, counts and
+ * site map, bit for bit, in O(ls ns + npatt log npatt) instead of the reference's O(npatt^2) insertion (host code:
+ * bytes only, runs once per data set).
+ *   ns, width        sequences; bytes per site and sequence (3 for codon data before encoding, else 1)
+ *   ls               sites (codons for codon data);   z[ns] row pointers, row j = ls*width bytes (com.z)
+ *   gene[ls]         gene label of every site (com.pose on entry) or NULL;   ngene  com.ngene
+ *   out: *npatt; posG[ngene+1] (com.posG); lgene[ngene] sites per gene (may be NULL); pose[ls] site -> pattern
+ *        (com.pose on return); fpatt[ls] (first *npatt entries used, com.fpatt); rep[ls] (first *npatt entries: the
+ *        site whose column represents each pattern -- the caller gathers com.z from it)                           */
+int pb200_compress_patterns(int ns, int width, long long ls, const unsigned char *const *z, const int *gene,
+                            int ngene, long long *npatt, long long *posG, long long *lgene, int *pose,
+                            double *fpatt, long long *rep);
+
 /* Multi-GPU: site patterns are sharded, one context (process) per GPU, and each evaluation
  * ends with ONE ncclAllReduce(sum) of the scalar -lnL.  Rank 0 makes an id, the launcher broadcasts the
  * 128 bytes, every rank calls pb200_comm_init.  NCCL is dlopen'ed at the first of these calls.           */

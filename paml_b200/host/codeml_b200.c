@@ -5,17 +5,24 @@
  *                   outside lfundG's own file) while the bare names in `com.plfun = lfun` / `== lfun` bind to ours;
  *   fx_r            is only ever called directly, always as fx_r(x, ..): the macro below pastes on the first
  *                   argument, so the reference's definition/prototype `fx_r(double x[], int np)` becomes fx_r_ref and
- *                   every call `fx_r(x, ..)` becomes fx_r_gpu (any other spelling fails to compile, loudly). */
+ *                   every call `fx_r(x, ..)` becomes fx_r_gpu (any other spelling fails to compile, loudly);
+ *   PatternWeight   (the step upstream of the path) the same way: `PatternWeight(void)` -> PatternWeight_ref, the call
+ *                   `PatternWeight()` -> PatternWeight_b200. */
 double lfun(double x[], int np);
 double lfundG(double x[], int np);
 int fx_r_gpu(double x[], int np);
+int PatternWeight_b200(void);
 #define lfun(a, b)   lfun_ref(a, b)
 #define lfundG(a, b) lfundG_ref(a, b)
 #define fx_r(a, b)   PBH_FXR_##a, b)
 #define PBH_FXR_x      fx_r_gpu(x
 #define PBH_FXR_double fx_r_ref(double
+#define PatternWeight(a) PBH_PW_##a
+#define PBH_PW_void PatternWeight_ref(void)
+#define PBH_PW_     PatternWeight_b200()
 #include "codeml.c"
 #undef lfun
 #undef lfundG
 #undef fx_r
+#undef PatternWeight
 #include "plfun_b200.inc"
