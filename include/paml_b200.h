@@ -103,6 +103,16 @@ int pb200_get_fhK(pb200_ctx *ctx, double *fhK);
 int pb200_pmat(pb200_ctx *ctx, int n, int set_kind, int nr, int nset, long long set_stride,
                const double *set_data, int nmat, const int *mat_set, const double *mat_t, double *P_out);
 
+/* Replaces eigenQREV (src/tools.c:5023-5110; eigenRealSym = Householder + QL, src/tools.c:5116-5309), the spectral
+ * decomposition eigenQcodon / eigenQaa / eigenQREVbase need once per parameter set:
+ * Q = S diag(pi) reversible, Q = U diag(Root) V with U V = I, Root in decreasing order, states with pi <= 1e-100
+ * dropped and re-inserted as identity like the reference.  njob matrices are solved by njob thread blocks of one
+ * launch (parallel-order two-sided Jacobi in shared memory).  The factors differ from the reference's by the signs of
+ * the eigenvectors (and by any rotation inside a repeated root); P(t) = U exp(Root t) V is the same to rounding.
+ *   Q[njob][n*n] row-major, pi[njob][n]  ->  Root[njob][n], U[njob][n*n], V[njob][n*n]; sweeps[njob] (may be NULL) */
+int pb200_eigen_qrev(pb200_ctx *ctx, int n, int njob, const double *Q, const double *pi, double *Root, double *U,
+                     double *V, int *sweeps);
+
 /* Replaces PatternWeight (src/treesub.c:1386-1516), the step that turns an alignment into the site patterns the
  * likelihood path consumes: the ls columns are collapsed, gene by gene, into their distinct patterns in ascending
  * strcmp order of (character + 1), each represented by the first site showing it -- the reference's order, counts and

@@ -16,6 +16,7 @@
 #include "prune_tma.cuh"
 #include "prune4.cuh"
 #include "prune4v2.cuh"
+#include "eigen.cuh"
 #include "plan.h"
 
 using namespace pb200;
@@ -122,6 +123,9 @@ struct pb200_ctx {
     DevBuf d_prog;
     // eval
     DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush, d_item_partial;
+    DevBuf d_eig;               // pb200_eigen_qrev: Q | pi | sets | info
+    void* h_eig = nullptr;      // its pinned mirror
+    size_t h_eig_cap = 0;
     bool fused_last = false;    // the last pruning launch already produced lnf and the sum
     void* h_stage = nullptr;
     size_t h_stage_cap = 0;
@@ -194,9 +198,10 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
                       &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs,
-                      &c->d_ops4, &c->d_tip_order, &c->d_zw};
+                      &c->d_ops4, &c->d_tip_order, &c->d_zw, &c->d_eig};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_eig) cudaFreeHost(c->h_eig);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1044,6 +1049,56 @@ extern "C" int pb200_measure_fp64_peak(pb200_ctx* c, double* dmma_tflops, double
     out.release();
     if (dmma_tflops) *dmma_tflops = best[0];
     if (dfma_tflops) *dfma_tflops = best[1];
+    return 0;
+}
+
+// Batched device eigen-solution of reversible rate matrices (eigen.cuh): host buffers in and out, synchronous.
+extern "C" int pb200_eigen_qrev(pb200_ctx* c, int n, int njob, const double* Q, const double* pi, double* Root, double* U,
+                                double* V, int* sweeps)
+{
+    if (!c || !Q || !pi || !Root || !U || !V) return fail("pb200_eigen_qrev: null argument");
+    if (n < 1 || n > EIG_MAXM || njob < 1) return fail("pb200_eigen_qrev: need 1 <= n <= %d and njob >= 1", EIG_MAXM);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t nn = (size_t)n * n, stride = (size_t)n + 2 * nn;
+    const size_t off_q = 0, off_pi = align16(off_q + (size_t)njob * nn * 8), off_sets = align16(off_pi + (size_t)njob * n * 8);
+    const size_t off_info = align16(off_sets + (size_t)njob * stride * 8), total = align16(off_info + (size_t)njob * 4);
+    if (total > c->h_eig_cap) {
+        if (c->h_eig) cudaFreeHost(c->h_eig);
+        c->h_eig = nullptr; c->h_eig_cap = 0;
+        CUDA_TRY(cudaMallocHost(&c->h_eig, total + total / 4));
+        c->h_eig_cap = total + total / 4;
+    }
+    if (c->d_eig.ensure(total)) return 1;
+    char* hs = (char*)c->h_eig;
+    char* ds = (char*)c->d_eig.p;
+    memcpy(hs + off_q, Q, (size_t)njob * nn * 8);
+    memcpy(hs + off_pi, pi, (size_t)njob * n * 8);
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, off_sets, cudaMemcpyHostToDevice, c->stream));
+    EigenParams p;
+    p.n = n; p.Q = (const double*)(ds + off_q); p.pi = (const double*)(ds + off_pi); p.sets = (double*)(ds + off_sets);
+    p.set_stride = (long long)stride; p.info = (int*)(ds + off_info); p.max_sweeps = 40;
+    const int m = n + (n & 1);
+    const size_t smem = (size_t)3 * m * (m + 1) * sizeof(double);
+    static bool attr_set[64] = {false};
+    if (c->device < 64 && !attr_set[c->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(eigen_qrev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * EIG_MAXM * (EIG_MAXM + 1) * 8));
+        attr_set[c->device] = true;
+    }
+    eigen_qrev_kernel<<<njob, EIG_THREADS, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(hs + off_sets, ds + off_sets, total - off_sets, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int* info = (const int*)(hs + off_info);
+    for (int j = 0; j < njob; j++) {
+        const double* set = (const double*)(hs + off_sets) + (size_t)j * stride;
+        memcpy(Root + (size_t)j * n, set, (size_t)n * 8);
+        memcpy(U + (size_t)j * nn, set + n, nn * 8);
+        memcpy(V + (size_t)j * nn, set + n + nn, nn * 8);
+        if (sweeps) sweeps[j] = info[j];
+    }
+    for (int j = 0; j < njob; j++)
+        if (info[j] < 0) return fail("pb200_eigen_qrev: matrix %d did not converge in %d Jacobi sweeps", j, -info[j] - 1);
     return 0;
 }
 

@@ -5,12 +5,14 @@
 // problem and re-inserted as identity rows/columns exactly as the reference does (src/tools.c:5055-5102).  The
 // reference solves the symmetric problem with Householder + implicit QL (eigenRealSym, src/tools.c:5116-5309), a
 // strictly sequential algorithm; here ONE CTA per matrix runs a parallel-order cyclic two-sided Jacobi iteration:
-// the m/2 disjoint rotations of a round-robin round are applied at once, thread (bi, bj) owning the 2x2 block in
-// rows of pair bi and columns of pair bj, double-buffered so that a round costs a single barrier.  Jacobi delivers
-// eigenvalues in working precision and orthogonal eigenvectors, so P(t) = U exp(t Root) V agrees with the
-// reference's to rounding (the decomposition itself is unique only up to order and sign: eigenvalues are sorted in
-// decreasing order like EigenSort, src/tools.c:5136-5158).  Several matrices (site classes, branch types) run as
-// several CTAs in the same launch; the sets are written straight into the staging area pt_kernel reads.
+// a round-robin round has m/2 disjoint pivot pairs; their rotations are computed by m/2 threads into shared memory,
+// then thread (bi, bj), bi <= bj, applies rotation bi from the left and rotation bj from the right to the 2x2 block
+// in rows of pair bi and columns of pair bj (and writes its mirror), reading matrix A_cur and writing A_next, while
+// the eigenvector columns are rotated in place by all threads: two barriers per round, m-1 rounds per sweep.
+// Jacobi delivers eigenvalues to working precision and orthogonal eigenvectors, so P(t) = U exp(t Root) V agrees
+// with the reference's to rounding (the decomposition itself is unique only up to order and sign: eigenvalues are
+// sorted in decreasing order like EigenSort, src/tools.c:5136-5158).  Several matrices (site classes, branch types,
+// branches) run as several CTAs of one launch; results are written in the UVROOT set layout pt_kernel reads.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -20,9 +22,7 @@ struct EigenParams {
     int n;                   // states (<= 64)
     const double* Q;         // [njob][n*n] row-major rate matrices
     const double* pi;        // [njob][n]
-    const double* scale;     // [njob] factor applied to Root (1/mean rate; 1 = none), src/codeml.c:3314-3321
-    const int* job_set;      // [njob] index of the spectral set job j produces
-    double* sets;            // [nset][set_stride]: Root[n], U[n*n], V[n*n]
+    double* sets;            // [njob][set_stride]: Root[n], U[n*n], V[n*n]
     long long set_stride;
     int* info;               // [njob] sweeps used (negative: not converged)
     int max_sweeps;
@@ -31,24 +31,15 @@ struct EigenParams {
 constexpr int EIG_THREADS = 1024;
 constexpr int EIG_MAXM = 64;
 
-__device__ __forceinline__ void jacobi_rotation(double app, double aqq, double apq, double& c, double& s, double& t)
-{
-    if (apq == 0.0) { c = 1.0; s = 0.0; t = 0.0; return; }
-    const double d = aqq - app;
-    const double r = sqrt(fma(d, d, 4.0 * apq * apq));
-    t = 2.0 * apq / (fabs(d) + r);
-    if (d < 0) t = -t;
-    c = 1.0 / sqrt(fma(t, t, 1.0));
-    s = t * c;
-}
-
 __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenParams p)
 {
     extern __shared__ __align__(16) double esm[];
     __shared__ int s_idx[EIG_MAXM];
     __shared__ int s_rank[EIG_MAXM];
     __shared__ double s_ps[EIG_MAXM];
-    __shared__ double s_red[2 * (EIG_THREADS / 32)];
+    __shared__ double s_c[EIG_MAXM / 2], s_s[EIG_MAXM / 2];
+    __shared__ int s_p[EIG_MAXM / 2], s_q[EIG_MAXM / 2];
+    __shared__ double s_red[EIG_THREADS / 32];
     __shared__ int s_nnew;
 
     const int job = blockIdx.x, tid = threadIdx.x, n = p.n;
@@ -68,7 +59,8 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
     double* A1 = A0 + m * LD;
     double* V = A1 + m * LD;
 
-    // A = pi^{1/2} Q pi^{-1/2}, built from the lower triangle of Q like the reference (src/tools.c:5047-5049, 5056-5066)
+    // A = pi^{1/2} Q pi^{-1/2}, built from the lower triangle of Q like the reference (src/tools.c:5047-5049, 5056-5066);
+    // an odd problem is padded with one zero row/column, which no rotation ever mixes with the rest
     for (int e = tid; e < m * m; e += EIG_THREADS) {
         const int i = e / m, j = e - i * m;
         double a = 0.0;
@@ -86,89 +78,91 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
 
     const int bi = tid >> 5, bj = tid & 31;
     const bool upper = (bi <= bj) && (bj < half);
-    // V work: lower-triangle threads, (half-1)/2 of them per pair, each taking a strided share of the m rows
-    const int per_pair = (half - 1) / 2 > 0 ? (half - 1) / 2 : 1;
-    int vpair = -1, vsub = 0;
-    if (half == 1) { if (tid == 1) { vpair = 0; vsub = 0; } }
-    else if (bi > bj && bi < half) {
-        const int li = bi * (bi - 1) / 2 + bj;
-        if (li < per_pair * half) { vpair = li / per_pair; vsub = li - vpair * per_pair; }
-    }
     const int nplayers = m - 1;
 
-    double frob2 = 0.0;
-    {
+    // block-wide sum of squares of the whole matrix (diag = true) or of its off-diagonal part
+    auto sumsq = [&](const double* A, bool with_diag) -> double {
         double loc = 0.0;
-        for (int e = tid; e < m * m; e += EIG_THREADS) { const int i = e / m, j = e - i * m; const double a = A0[i * LD + j]; loc += a * a; }
+        for (int e = tid; e < m * m; e += EIG_THREADS) {
+            const int i = e / m, j = e - i * m;
+            if (with_diag || i != j) { const double a = A[i * LD + j]; loc += a * a; }
+        }
         for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
         if ((tid & 31) == 0) s_red[tid >> 5] = loc;
         __syncthreads();
-        for (int w = 0; w < EIG_THREADS / 32; w++) frob2 += s_red[w];
+        double tot = 0.0;
+        for (int w = 0; w < EIG_THREADS / 32; w++) tot += s_red[w];
         __syncthreads();
-    }
+        return tot;
+    };
+    const double frob2 = sumsq(A0, true);
 
     int sweeps = 0;
     bool converged = (m < 2) || frob2 == 0.0;
+    bool last = false;                       // the sweep that starts below the quadratic-convergence threshold is the last
     double* Ac = A0;
     double* An = A1;
     while (!converged && sweeps < p.max_sweeps) {
         for (int r = 0; r < nplayers; r++) {
             // round-robin pairing of round r: pair 0 = (m-1, r), pair k = (r+k, r-k) mod (m-1)
-            auto pair_of = [&](int k, int& pp, int& qq) {
+            if (tid < half) {
                 int a, b;
-                if (k == 0) { a = m - 1; b = r % nplayers; }
-                else { a = (r + k) % nplayers; b = (r - k + 2 * nplayers) % nplayers; }
-                pp = a < b ? a : b; qq = a < b ? b : a;
-            };
+                if (tid == 0) { a = m - 1; b = r; }
+                else { a = (r + tid) % nplayers; b = (r - tid + nplayers) % nplayers; }
+                const int pp = a < b ? a : b, qq = a < b ? b : a;
+                const double app = Ac[pp * LD + pp], aqq = Ac[qq * LD + qq], apq = Ac[pp * LD + qq];
+                double c = 1.0, s = 0.0;
+                if (apq != 0.0) {
+                    const double d = aqq - app;
+                    const double rr = sqrt(fma(d, d, 4.0 * apq * apq));
+                    if (rr > 0.0) {                         // (rr == 0: d = 0 and apq^2 underflowed -- nothing to rotate)
+                        double t = 2.0 * apq / (fabs(d) + rr);
+                        if (d < 0) t = -t;
+                        c = 1.0 / sqrt(fma(t, t, 1.0));
+                        s = t * c;
+                    }
+                }
+                s_c[tid] = c; s_s[tid] = s; s_p[tid] = pp; s_q[tid] = qq;
+            }
+            __syncthreads();
             if (upper) {
-                int p1, q1, p2, q2;
-                pair_of(bi, p1, q1); pair_of(bj, p2, q2);
-                double c1, s1, t1, c2, s2, t2;
-                const double app = Ac[p1 * LD + p1], aqq = Ac[q1 * LD + q1], apq = Ac[p1 * LD + q1];
-                jacobi_rotation(app, aqq, apq, c1, s1, t1);
+                const int p1 = s_p[bi], q1 = s_q[bi], p2 = s_p[bj], q2 = s_q[bj];
+                const double c1 = s_c[bi], s1 = s_s[bi], c2 = s_c[bj], s2 = s_s[bj];
+                const double apu = Ac[p1 * LD + p2], apw = Ac[p1 * LD + q2], aqu = Ac[q1 * LD + p2], aqw = Ac[q1 * LD + q2];
+                // rows of pair 1 rotated (J^T from the left), then columns of pair 2 (J from the right)
+                const double rpu = c1 * apu - s1 * aqu, rqu = s1 * apu + c1 * aqu;
+                const double rpw = c1 * apw - s1 * aqw, rqw = s1 * apw + c1 * aqw;
+                const double npu = c2 * rpu - s2 * rpw, npw = s2 * rpu + c2 * rpw;
+                const double nqu = c2 * rqu - s2 * rqw, nqw = s2 * rqu + c2 * rqw;
                 if (bi == bj) {
-                    An[p1 * LD + p1] = app - t1 * apq;
-                    An[q1 * LD + q1] = aqq + t1 * apq;
-                    An[p1 * LD + q1] = 0.0; An[q1 * LD + p1] = 0.0;
+                    An[p1 * LD + p1] = npu; An[q1 * LD + q1] = nqw;
+                    An[p1 * LD + q1] = 0.0; An[q1 * LD + p1] = 0.0;   // annihilated by construction
                 }
                 else {
-                    jacobi_rotation(Ac[p2 * LD + p2], Ac[q2 * LD + q2], Ac[p2 * LD + q2], c2, s2, t2);
-                    const double apu = Ac[p1 * LD + p2], apw = Ac[p1 * LD + q2], aqu = Ac[q1 * LD + p2], aqw = Ac[q1 * LD + q2];
-                    const double rpu = c1 * apu - s1 * aqu, rqu = s1 * apu + c1 * aqu;
-                    const double rpw = c1 * apw - s1 * aqw, rqw = s1 * apw + c1 * aqw;
-                    const double npu = c2 * rpu - s2 * rpw, npw = s2 * rpu + c2 * rpw;
-                    const double nqu = c2 * rqu - s2 * rqw, nqw = s2 * rqu + c2 * rqw;
                     An[p1 * LD + p2] = npu; An[p2 * LD + p1] = npu;
                     An[p1 * LD + q2] = npw; An[q2 * LD + p1] = npw;
                     An[q1 * LD + p2] = nqu; An[p2 * LD + q1] = nqu;
                     An[q1 * LD + q2] = nqw; An[q2 * LD + q1] = nqw;
                 }
             }
-            else if (vpair >= 0) {
-                int pp, qq;
-                pair_of(vpair, pp, qq);
-                double c, s, t;
-                jacobi_rotation(Ac[pp * LD + pp], Ac[qq * LD + qq], Ac[pp * LD + qq], c, s, t);
-                for (int i = vsub; i < m; i += per_pair) {
-                    const double vp = V[i * LD + pp], vq = V[i * LD + qq];
-                    V[i * LD + pp] = c * vp - s * vq;
-                    V[i * LD + qq] = s * vp + c * vq;
-                }
+            // eigenvector columns of every pair, in place (pairs are disjoint): item = (pair, row)
+            for (int it = tid; it < half * m; it += EIG_THREADS) {
+                const int k = it / m, i = it - k * m;
+                const int pp = s_p[k], qq = s_q[k];
+                const double c = s_c[k], s = s_s[k];
+                const double vp = V[i * LD + pp], vq = V[i * LD + qq];
+                V[i * LD + pp] = c * vp - s * vq;
+                V[i * LD + qq] = s * vp + c * vq;
             }
             __syncthreads();
             double* tmp = Ac; Ac = An; An = tmp;
         }
         sweeps++;
-        // convergence: off-diagonal Frobenius norm against the whole matrix
-        double loc = 0.0;
-        for (int e = tid; e < m * m; e += EIG_THREADS) { const int i = e / m, j = e - i * m; if (i != j) { const double a = Ac[i * LD + j]; loc += a * a; } }
-        for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
-        if ((tid & 31) == 0) s_red[tid >> 5] = loc;
-        __syncthreads();
-        double off2 = 0.0;
-        for (int w = 0; w < EIG_THREADS / 32; w++) off2 += s_red[w];
-        __syncthreads();
-        converged = off2 <= 1e-33 * frob2;          // off <= 3e-17 |A|_F
+        // Jacobi converges quadratically: once the off-diagonal norm is below 1e-9 |A|_F one more sweep takes it to the
+        // rounding floor.  (A plain "off <= eps |A|" test would never fire: the floor itself is ~1e-15 |A|_F.)
+        const double off2 = sumsq(Ac, false);
+        if (last || off2 <= 1e-30 * frob2) converged = true;
+        else if (off2 <= 1e-18 * frob2) last = true;
     }
 
     // eigenvalues in decreasing order (ties: by index), like EigenSort
@@ -180,16 +174,15 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
     }
     __syncthreads();
 
-    double* set = p.sets + (size_t)p.job_set[job] * p.set_stride;
+    double* set = p.sets + (size_t)job * p.set_stride;
     double* Root = set;
     double* U = set + n;
     double* Vo = set + n + (size_t)n * n;
-    const double sc = p.scale ? p.scale[job] : 1.0;
     // dropped states: Root 0, identity row/column (src/tools.c:5070-5101)
     for (int e = tid; e < n * n; e += EIG_THREADS) { const int i = e / n, j = e - i * n; U[e] = (i == j) ? 1.0 : 0.0; Vo[e] = (i == j) ? 1.0 : 0.0; }
     if (tid < n) Root[tid] = 0.0;
     __syncthreads();
-    if (tid < nnew) Root[s_idx[s_rank[tid]]] = Ac[tid * LD + tid] * sc;
+    if (tid < nnew) Root[s_idx[s_rank[tid]]] = Ac[tid * LD + tid];
     for (int e = tid; e < nnew * nnew; e += EIG_THREADS) {
         const int i = e / nnew, k = e - i * nnew;          // component i of eigenvector k
         const double v = V[i * LD + k];

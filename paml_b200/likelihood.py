@@ -156,6 +156,18 @@ class TreeLikelihood:
                                  _ptr(mat_set, C.c_int), _ptr(mat_t, C.c_double), _ptr(out, C.c_double)))
         return out
 
+    def eigen_qrev(self, Q, pi):
+        """pb200_eigen_qrev: Q [njob, n, n] (or [n, n]), pi [njob, n] -> Root [njob, n], U, V [njob, n, n], sweeps [njob]."""
+        Q = np.ascontiguousarray(Q, np.float64)
+        pi = np.ascontiguousarray(pi, np.float64)
+        if Q.ndim == 2:
+            Q = Q[None]; pi = pi[None]
+        njob, n = Q.shape[0], Q.shape[1]
+        Root = np.zeros((njob, n)); U = np.zeros((njob, n, n)); V = np.zeros((njob, n, n)); sw = np.zeros(njob, np.int32)
+        check(self._L.pb200_eigen_qrev(self._ctx, C.c_int(n), C.c_int(njob), _ptr(Q, C.c_double), _ptr(pi, C.c_double),
+                                       _ptr(Root, C.c_double), _ptr(U, C.c_double), _ptr(V, C.c_double), _ptr(sw, C.c_int)))
+        return Root, U, V, sw
+
     # -- multi-GPU --------------------------------------------------------------------------------
     @staticmethod
     def nccl_unique_id():

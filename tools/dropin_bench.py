@@ -1,0 +1,43 @@
+"""Evaluations per second of the drop-in itself: codeml_b200 fitting kappa and omega (branch lengths fixed) on a
+BASELINE-config-2-shaped data set, i.e. the whole com.plfun call as ming2 drives it -- SetParameters (host Q
+construction + eigen-solution), gather, H2D, kernels, D2H.  Run once with the reference's host eigenQREV
+(PB200_EIGEN=host) and once with the device Jacobi solver (default), and, if present, the unmodified reference.
+usage: python tools/dropin_bench.py [npatt]"""
+import os, re, subprocess, sys, tempfile, time
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from paml_b200 import paml_io, simulate
+
+npatt = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+p = simulate.codon_m0_problem(npatt=npatt, seed=13147)
+
+
+def run(exe, env, fit):
+    d = tempfile.mkdtemp(prefix="pb200_db_")
+    paml_io.write_pattern_files(p, d + "/s")
+    paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                             extra=dict(fix_kappa=0, fix_omega=0, fix_blength=2))
+    if not fit:
+        open(d + "/in.codeml", "w").write("-1 2.0 0.4\n")
+    t0 = time.time()
+    r = subprocess.run([exe, "run.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, env=dict(os.environ, **env))
+    dt = time.time() - t0
+    m = re.search(r"(\d+) lfun", r.stdout)
+    l = re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d + "/mlc").read())
+    return dt, int(m.group(1)) if m else 0, float(l[-1]) if l else float("nan")
+
+
+for tag, exe, env in (("drop-in, device eigen", REPO + "/paml_b200/bin/codeml_b200", {}),
+                      ("drop-in, host eigen (reference eigenQREV)", REPO + "/paml_b200/bin/codeml_b200", {"PB200_EIGEN": "host"}),
+                      ("unmodified reference", REPO + "/oracle/_ref/codeml", {})):
+    if not os.path.exists(exe):
+        continue
+    if "reference" == tag.split()[-1] and npatt > 20000:
+        print("%-45s skipped (npatt > 20000 takes minutes on one core)" % tag)
+        continue
+    t1, n1, l1 = run(exe, env, False)
+    t2, n2, l2 = run(exe, env, True)
+    per = (t2 - t1) / max(1, n2 - n1)
+    print("%-45s 1 eval: %.2f s; fit: %.2f s, %d lfun, lnL %.6f -> %.3f ms per evaluation = %.0f evaluations/s"
+          % (tag, t1, t2, n2, l2, per * 1e3, 1 / per if per > 0 else float("nan")))
