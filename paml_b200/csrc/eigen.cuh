@@ -8,7 +8,8 @@
 // a round-robin round has m/2 disjoint pivot pairs; their rotations are computed by m/2 threads into shared memory,
 // then thread (bi, bj), bi <= bj, applies rotation bi from the left and rotation bj from the right to the 2x2 block
 // in rows of pair bi and columns of pair bj (and writes its mirror), reading matrix A_cur and writing A_next, while
-// the eigenvector columns are rotated in place by all threads: two barriers per round, m-1 rounds per sweep.
+// the eigenvector columns are rotated in place by all threads: two barriers per round, m-1 rounds per sweep.  The
+// rotation is computed with two FP64 reciprocal square roots and no division (it is the round's critical path).
 // Jacobi delivers eigenvalues to working precision and orthogonal eigenvectors, so P(t) = U exp(t Root) V agrees
 // with the reference's to rounding (the decomposition itself is unique only up to order and sign: eigenvalues are
 // sorted in decreasing order like EigenSort, src/tools.c:5136-5158).  Several matrices (site classes, branch types,
@@ -72,20 +73,26 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
             }
         }
         A0[i * LD + j] = a; A1[i * LD + j] = a;
-        V[i * LD + j] = (i == j) ? 1.0 : 0.0;
+        V[i * LD + j] = (i == j) ? 1.0 : 0.0;                 // eigenvectors, COLUMN-major: V[k * LD + i] = component i of vector k
     }
     __syncthreads();
 
     const int bi = tid >> 5, bj = tid & 31;
     const bool upper = (bi <= bj) && (bj < half);
     const int nplayers = m - 1;
+    // this thread's eigenvector items (pair index, component): consecutive lanes take consecutive components -> conflict-free
+    //: half * m <= 2048 items over 1024 threads
+    int vk0 = -1, vi0 = 0, vk1 = -1, vi1 = 0;
+    if (tid < half * m) { vk0 = tid / m; vi0 = tid - vk0 * m; }
+    if (tid + EIG_THREADS < half * m) { vk1 = (tid + EIG_THREADS) / m; vi1 = tid + EIG_THREADS - vk1 * m; }
 
-    // block-wide sum of squares of the whole matrix (diag = true) or of its off-diagonal part
+    // block-wide sum of squares of the symmetric matrix held in the upper triangle, with or without its diagonal
     auto sumsq = [&](const double* A, bool with_diag) -> double {
         double loc = 0.0;
         for (int e = tid; e < m * m; e += EIG_THREADS) {
             const int i = e / m, j = e - i * m;
-            if (with_diag || i != j) { const double a = A[i * LD + j]; loc += a * a; }
+            if (i < j) { const double a = A[i * LD + j]; loc += 2.0 * a * a; }
+            else if (i == j && with_diag) { const double a = A[i * LD + j]; loc += a * a; }
         }
         for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
         if ((tid & 31) == 0) s_red[tid >> 5] = loc;
@@ -108,19 +115,24 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
             if (tid < half) {
                 int a, b;
                 if (tid == 0) { a = m - 1; b = r; }
-                else { a = (r + tid) % nplayers; b = (r - tid + nplayers) % nplayers; }
+                else { a = r + tid; if (a >= nplayers) a -= nplayers; b = r - tid; if (b < 0) b += nplayers; }
                 const int pp = a < b ? a : b, qq = a < b ? b : a;
                 const double app = Ac[pp * LD + pp], aqq = Ac[qq * LD + qq], apq = Ac[pp * LD + qq];
                 double c = 1.0, s = 0.0;
-                if (apq != 0.0) {
-                    const double d = aqq - app;
-                    const double rr = sqrt(fma(d, d, 4.0 * apq * apq));
-                    if (rr > 0.0) {                         // (rr == 0: d = 0 and apq^2 underflowed -- nothing to rotate)
-                        double t = 2.0 * apq / (fabs(d) + rr);
-                        if (d < 0) t = -t;
-                        c = 1.0 / sqrt(fma(t, t, 1.0));
-                        s = t * c;
-                    }
+                // inner rotation (|theta| <= pi/4) annihilating a_pq: tan 2theta = 2 a_pq / (a_qq - a_pp).  Formulated with two
+                // reciprocal square roots and no division (FP64 div / sqrt are long dependent sequences and this
+                // thread is the critical path of the round): cos 2theta = |d| / h, sin 2theta = sgn(d) 2 a_pq / h,
+                // h = hypot(d, 2 a_pq); cos theta = sqrt((1 + cos 2theta) / 2), sin theta = sin 2theta / (2 cos theta).
+                const double d = aqq - app, two_apq = 2.0 * apq;
+                const double h2 = fma(d, d, two_apq * two_apq);
+                if (apq != 0.0 && h2 > 1e-290) {            // (below: nothing to rotate in working precision)
+                    const double ih = rsqrt(h2);
+                    const double cos2 = fabs(d) * ih;
+                    const double sin2 = (d < 0 ? -two_apq : two_apq) * ih;
+                    const double x = 0.5 + 0.5 * cos2;      // in [0.5, 1]
+                    const double ix = rsqrt(x);
+                    c = x * ix;
+                    s = 0.5 * sin2 * ix;
                 }
                 s_c[tid] = c; s_s[tid] = s; s_p[tid] = pp; s_q[tid] = qq;
             }
@@ -128,31 +140,37 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
             if (upper) {
                 const int p1 = s_p[bi], q1 = s_q[bi], p2 = s_p[bj], q2 = s_q[bj];
                 const double c1 = s_c[bi], s1 = s_s[bi], c2 = s_c[bj], s2 = s_s[bj];
-                const double apu = Ac[p1 * LD + p2], apw = Ac[p1 * LD + q2], aqu = Ac[q1 * LD + p2], aqw = Ac[q1 * LD + q2];
+                // A is symmetric: only [min][max] is kept up to date (half the stores, no strided mirror writes)
+                const int ipu = p1 < p2 ? p1 * LD + p2 : p2 * LD + p1, ipw = p1 < q2 ? p1 * LD + q2 : q2 * LD + p1;
+                const int iqu = q1 < p2 ? q1 * LD + p2 : p2 * LD + q1, iqw = q1 < q2 ? q1 * LD + q2 : q2 * LD + q1;
+                const double apu = Ac[ipu], apw = Ac[ipw], aqu = Ac[iqu], aqw = Ac[iqw];
                 // rows of pair 1 rotated (J^T from the left), then columns of pair 2 (J from the right)
                 const double rpu = c1 * apu - s1 * aqu, rqu = s1 * apu + c1 * aqu;
                 const double rpw = c1 * apw - s1 * aqw, rqw = s1 * apw + c1 * aqw;
                 const double npu = c2 * rpu - s2 * rpw, npw = s2 * rpu + c2 * rpw;
                 const double nqu = c2 * rqu - s2 * rqw, nqw = s2 * rqu + c2 * rqw;
                 if (bi == bj) {
-                    An[p1 * LD + p1] = npu; An[q1 * LD + q1] = nqw;
-                    An[p1 * LD + q1] = 0.0; An[q1 * LD + p1] = 0.0;   // annihilated by construction
+                    An[ipu] = npu; An[iqw] = nqw;
+                    An[ipw] = 0.0;                          // a_pq, annihilated by construction (ipw == [p1][q1])
                 }
                 else {
-                    An[p1 * LD + p2] = npu; An[p2 * LD + p1] = npu;
-                    An[p1 * LD + q2] = npw; An[q2 * LD + p1] = npw;
-                    An[q1 * LD + p2] = nqu; An[p2 * LD + q1] = nqu;
-                    An[q1 * LD + q2] = nqw; An[q2 * LD + q1] = nqw;
+                    An[ipu] = npu; An[ipw] = npw; An[iqu] = nqu; An[iqw] = nqw;
                 }
             }
-            // eigenvector columns of every pair, in place (pairs are disjoint): item = (pair, row)
-            for (int it = tid; it < half * m; it += EIG_THREADS) {
-                const int k = it / m, i = it - k * m;
-                const int pp = s_p[k], qq = s_q[k];
-                const double c = s_c[k], s = s_s[k];
-                const double vp = V[i * LD + pp], vq = V[i * LD + qq];
-                V[i * LD + pp] = c * vp - s * vq;
-                V[i * LD + qq] = s * vp + c * vq;
+            // eigenvector columns of every pair, in place (pairs are disjoint): item = (pair, row), at most two per thread
+            if (vk0 >= 0) {
+                const int pp = s_p[vk0], qq = s_q[vk0];
+                const double c = s_c[vk0], s = s_s[vk0];
+                const double vp = V[pp * LD + vi0], vq = V[qq * LD + vi0];
+                V[pp * LD + vi0] = c * vp - s * vq;
+                V[qq * LD + vi0] = s * vp + c * vq;
+            }
+            if (vk1 >= 0) {
+                const int pp = s_p[vk1], qq = s_q[vk1];
+                const double c = s_c[vk1], s = s_s[vk1];
+                const double vp = V[pp * LD + vi1], vq = V[qq * LD + vi1];
+                V[pp * LD + vi1] = c * vp - s * vq;
+                V[qq * LD + vi1] = s * vp + c * vq;
             }
             __syncthreads();
             double* tmp = Ac; Ac = An; An = tmp;
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
     if (tid < nnew) Root[s_idx[s_rank[tid]]] = Ac[tid * LD + tid];
     for (int e = tid; e < nnew * nnew; e += EIG_THREADS) {
         const int i = e / nnew, k = e - i * nnew;          // component i of eigenvector k
-        const double v = V[i * LD + k];
+        const double v = V[k * LD + i];
         const int col = s_idx[s_rank[k]];                   // where eigen-pair k goes
         U[s_idx[i] * n + col] = v / s_ps[i];
         Vo[col * n + s_idx[i]] = v * s_ps[i];

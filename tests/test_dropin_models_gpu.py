@@ -141,6 +141,32 @@ def test_codeml_free_ratio_fixed_point(tmp_path):
     _close(_both(tmp_path, "codeml", write, "mlc"), 1e-9)
 
 
+def test_codeml_m3_five_classes_fixed_point(tmp_path):
+    """NSsites = 3 with K = 5: five eigenQcodon calls per evaluation (SetPSiteClass, src/treesub.c:7677-7686), which the
+    drop-in queues and solves in ONE device launch (pb200_eigen_qrev, five thread blocks); also run with the reference's
+    host solver (PB200_EIGEN=host) and with every solution forced to the device (PB200_EIGEN=device)."""
+    p = simulate.codon_sites_problem(ns=7, npatt=150, seed=42)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", NSsites=3, kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=2, ncatG=5))
+        with open(d + "/in.codeml", "w") as f:
+            f.write("-1  2.0  0.3 0.25 0.2 0.15  0.05 0.3 0.8 1.5 3.0\n")
+    res = _both(tmp_path, "codeml", write, "mlc")
+    _close(res, 1e-9)
+    exe = os.path.join(BIN, "codeml_b200")
+    for mode in ("host", "device"):
+        d = tmp_path / mode
+        d.mkdir()
+        write(str(d))
+        r = subprocess.run([exe, "run.ctl"], cwd=str(d), stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=900, env=dict(os.environ, PB200_EIGEN=mode))
+        assert r.returncode == 0, r.stdout[-2000:]
+        v = _lnl(str(d / "mlc"))
+        assert abs(v - res["ref"][0]) <= 1e-9 * abs(res["ref"][0]), (mode, v, res["ref"][0])
+
+
 def _numbers(path):
     """Every decimal number of a report, with the number of decimals it was printed with."""
     out = []

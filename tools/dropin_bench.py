@@ -25,7 +25,8 @@ def run(exe, env, fit):
     dt = time.time() - t0
     m = re.search(r"(\d+) lfun", r.stdout)
     l = re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d + "/mlc").read())
-    return dt, int(m.group(1)) if m else 0, float(l[-1]) if l else float("nan")
+    prof = re.search(r"paml_b200 profile: (.*)", r.stdout)
+    return dt, int(m.group(1)) if m else 0, float(l[-1]) if l else float("nan"), prof.group(1) if prof else ""
 
 
 for tag, exe, env in (("drop-in, device eigen", REPO + "/paml_b200/bin/codeml_b200", {}),
@@ -36,8 +37,11 @@ for tag, exe, env in (("drop-in, device eigen", REPO + "/paml_b200/bin/codeml_b2
     if "reference" == tag.split()[-1] and npatt > 20000:
         print("%-45s skipped (npatt > 20000 takes minutes on one core)" % tag)
         continue
-    t1, n1, l1 = run(exe, env, False)
-    t2, n2, l2 = run(exe, env, True)
+    env = dict(env, PB200_PROFILE="1")
+    t1, n1, l1, _ = run(exe, env, False)
+    t2, n2, l2, prof = run(exe, env, True)
     per = (t2 - t1) / max(1, n2 - n1)
-    print("%-45s 1 eval: %.2f s; fit: %.2f s, %d lfun, lnL %.6f -> %.3f ms per evaluation = %.0f evaluations/s"
-          % (tag, t1, t2, n2, l2, per * 1e3, 1 / per if per > 0 else float("nan")))
+    print("%-45s fit: %.2f s wall, %d lfun, lnL %.6f; wall difference to a 1-evaluation run: %.3f ms per evaluation"
+          % (tag, t2, n2, l2, per * 1e3))
+    if prof:
+        print("    in-process: " + prof)
