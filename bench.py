@@ -63,7 +63,7 @@ class ClockSampler:
     falls back to `nvidia-smi -lms` (B200_PROFILING.md recipe) if NVML is unavailable."""
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.stop_flag, self.t, self.h = gpu_index, [], False, None, None
+        self.idx, self.rows, self.stop_flag, self.t, self.h, self.skip = gpu_index, [], False, None, None, 0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -95,6 +95,12 @@ class ClockSampler:
             return
         self.t = threading.Thread(target=self._loop, daemon=True)
         self.t.start()
+        # the first NVML queries pay one-off driver costs (tens of ms): let the loop reach its steady ~0.1 ms period before
+        # the timed region opens, and count only the samples taken from here on
+        t0 = time.time()
+        while len(self.rows) < 3 and time.time() - t0 < 1.0:
+            time.sleep(0.001)
+        self.skip = len(self.rows)
 
     def stop(self):
         if self.nv is None or self.t is None:
@@ -106,6 +112,8 @@ class ClockSampler:
             smax = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception:
             smax = None
+        if len(self.rows) > self.skip:
+            self.rows = self.rows[self.skip:]
         if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=smax, reasons=["no samples"])
         names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -186,6 +194,37 @@ def time_oracle_port(p, sample):
     oracle.lnl(q)
     t0 = time.time(); oracle.lnl(q); dt = time.time() - t0
     return dict(updates_per_s=sample * (p.nnode - p.ns) / dt, sample=sample, sec_per_eval=dt, nproc=1)
+
+
+def time_dropin(p):
+    """BASELINE metric (ii), complete com.plfun calls per second: the drop-in binary (the reference's own driver, ming2 and
+    SetParameters incl. the host Q construction / eigen-solution, with lfun on the GPU) fitting kappa and omega on the
+    workload; its in-process profile (PB200_PROFILE) gives the wall time per call and where it goes."""
+    import re
+    import tempfile
+    from paml_b200 import paml_io
+    exe = os.path.join(REPO, "paml_b200", "bin", "codeml_b200")
+    if not os.path.exists(exe):
+        return None
+    d = tempfile.mkdtemp(prefix="pb200_dropin_")
+    paml_io.write_pattern_files(p, d + "/s")
+    paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                             extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1))
+    try:
+        r = subprocess.run([exe, "run.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=600, env=dict(os.environ, PB200_PROFILE="1"))
+    except subprocess.TimeoutExpired:
+        return None
+    m = re.search(r"then (\d+) evaluations, ([\d.]+) ms each.*SetParameters ([\d.]+) ms, gather ([\d.]+) ms, GPU \(H2D \+ kernels \+ D2H\) "
+                  r"([\d.]+) ms, per-pattern outputs ([\d.]+) ms", r.stdout)
+    if r.returncode != 0 or not m:
+        return None
+    n, each, sp, ga, gpu, outp = int(m.group(1)), *[float(m.group(i)) for i in range(2, 7)]
+    memo = re.search(r"eigen-solutions remembered (\d+), solved (\d+)", r.stdout)
+    return dict(what="codeml_b200 (reference driver + ming2, lfun on the GPU) fitting branch lengths, kappa and omega on the workload",
+                evaluations=n, ms_per_plfun_call=sp + ga + gpu, evals_per_sec=1e3 / (sp + ga + gpu),
+                ms=dict(SetParameters_host=sp, gather=ga, gpu_h2d_kernels_d2h=gpu, per_pattern_outputs_final_calls=outp),
+                eigen_memo=dict(remembered=int(memo.group(1)), solved=int(memo.group(2))) if memo else None)
 
 
 def run_reference_arm(args, rank, world):
@@ -371,6 +410,10 @@ def main():
                                         sample="%d of the %d patterns, %d lfun evaluations (unmodified codeml, gcc -O3)"
                                                % (r["sample"], p.npatt, r.get("reps", 1)),
                                         sec_per_eval=r["sec_per_eval"])
+            d = time_dropin(p)
+            if d:
+                line["evals_per_sec"]["dropin_plfun"] = d["evals_per_sec"]
+                line["dropin"] = d
         print(json.dumps(line))
     tl.close()
     if world > 1:

@@ -1,0 +1,6 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_dropin_gpu.py tests/test_dropin_models_gpu.py -m gpu -q 2>&1 | tail -30 > gpurun_out/c10_dropin_tests.log
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/c10_bench.json 2> gpurun_out/c10_bench.err
+timeout 300 python tools/dropin_bench.py 100000 m0 > gpurun_out/c10_dropin_m0.log 2>&1
+timeout 600 python tools/dropin_bench.py 50000 sites > gpurun_out/c10_dropin_sites.log 2>&1
+tail -8 gpurun_out/c10_dropin_tests.log; cat gpurun_out/c10_bench.json; tail -3 gpurun_out/c10_bench.err; cat gpurun_out/c10_dropin_m0.log gpurun_out/c10_dropin_sites.log

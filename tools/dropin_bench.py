@@ -2,23 +2,30 @@
 BASELINE-config-2-shaped data set, i.e. the whole com.plfun call as ming2 drives it -- SetParameters (host Q
 construction + eigen-solution), gather, H2D, kernels, D2H.  Run once with the reference's host eigenQREV
 (PB200_EIGEN=host) and once with the device Jacobi solver (default), and, if present, the unmodified reference.
-usage: python tools/dropin_bench.py [npatt]"""
+usage: python tools/dropin_bench.py [npatt] [m0|sites]   (sites: BASELINE config 3 shape, 32 taxa, NSsites = 3 with 4 classes:
+four eigen-solutions per evaluation, which the drop-in batches into one device launch)"""
 import os, re, subprocess, sys, tempfile, time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from paml_b200 import paml_io, simulate
 
 npatt = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-p = simulate.codon_m0_problem(npatt=npatt, seed=13147)
+kind = sys.argv[2] if len(sys.argv) > 2 else "m0"
+if kind == "m0":
+    p = simulate.codon_m0_problem(npatt=npatt, seed=13147)
+    EXTRA, INIT = dict(fix_kappa=0, fix_omega=0, fix_blength=2), "-1 2.0 0.4\n"
+else:
+    p = simulate.codon_sites_problem(ns=32, npatt=npatt, seed=13149)
+    EXTRA, INIT = dict(fix_kappa=0, fix_omega=0, fix_blength=2, NSsites=3, ncatG=4), "-1 2.0  0.4 0.3 0.2  0.05 0.3 1.0 2.5\n"
 
 
 def run(exe, env, fit):
     d = tempfile.mkdtemp(prefix="pb200_db_")
     paml_io.write_pattern_files(p, d + "/s")
     paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
-                             extra=dict(fix_kappa=0, fix_omega=0, fix_blength=2))
+                             extra=EXTRA)
     if not fit:
-        open(d + "/in.codeml", "w").write("-1 2.0 0.4\n")
+        open(d + "/in.codeml", "w").write(INIT)
     t0 = time.time()
     r = subprocess.run([exe, "run.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, env=dict(os.environ, **env))
