@@ -113,6 +113,34 @@ int pb200_pmat(pb200_ctx *ctx, int n, int set_kind, int nr, int nset, long long 
 int pb200_eigen_qrev(pb200_ctx *ctx, int n, int njob, const double *Q, const double *pi, double *Root, double *U,
                      double *V, int *sweeps);
 
+/* The one-branch-at-a-time optimiser (`method = 1`: minbranches, src/treesub.c:8039-8123) needs what the evaluation
+ * kernels never write: every internal node's conditional vectors, RESIDENT in HBM ([class][internal node][pattern]
+ * [state], the layout of com.conP, src/treesub.c:3518-3530).
+ *
+ * pb200_cond_update replaces updateconP / ConditionalPNode with com.oldconP (src/treesub.c:7982-8036, src/codeml.c:
+ * 3526-3582): it recomputes the listed internal nodes, in the order given (sons before fathers), under the CURRENT
+ * rooting described by the son lists, from P(t) of the branches they read; nodes not listed keep their vectors.
+ *   nclass               1, or com.ncatG when com.conPSiteClass
+ *   set_kind .. branch_t as in pb200_eval, for the current rooting (entry of node i = the branch above i)
+ *   upd_node[nupd], upd_nson[nupd], upd_sons[nupd][maxsons]   nodes to recompute and their sons (tips: ids < ns)
+ *   scale_flags[nnode]   com.nodeScale or NULL: NodeScale (src/treesub.c:7200-7230) is applied at flagged nodes
+ * The spectral sets stay resident for the pb200_branch_lnl calls that follow.
+ *
+ * pb200_branch_lnl replaces lfunt / lfuntdd / lfunt_SiteClass / lfuntdd_SiteClass (src/treesub.c:8127-8543) for the
+ * branch b -> a at length t (the tree rooted at b, a internal, b a tip or internal):
+ *   f_h = sum_classes pK sum_i pi_i L_b(i) sum_j P_ij L_a(j),  P = sum_k C_ijk exp(t mult Root_k)  (and dP/dt, d2P/dt2)
+ *   mult[nclass]         rgene * _rateSite * Qfactor_NS_branch, set_of_class[nclass] the spectral set of branch a per class
+ *   semantics            0 = lfunt/lfuntdd (one class), 1 = the _SiteClass forms (freqK, per-class scale bookkeeping)
+ *   out[3]               -lnL, d(-lnL)/dt, d2(-lnL)/dt2 (the last two only when want_dd)
+ * pb200_cond_get copies one node's resident vectors / the scale factors back (tests).                              */
+int pb200_cond_update(pb200_ctx *ctx, int nclass, int set_kind, int nr, int nset, long long set_stride,
+                      const double *set_data, const int *branch_set, const double *branch_t, int nupd,
+                      const int *upd_node, const int *upd_nson, const int *upd_sons, int maxsons,
+                      const unsigned char *scale_flags);
+int pb200_branch_lnl(pb200_ctx *ctx, int nclass, const double *freqK, int a, int b, double t, const double *mult,
+                     const int *set_of_class, const double *pi, int semantics, int want_dd, double out[3]);
+int pb200_cond_get(pb200_ctx *ctx, int node, double *cond, double *scaleF);
+
 /* Replaces PatternWeight (src/treesub.c:1386-1516), the step that turns an alignment into the site patterns the
  * likelihood path consumes: the ls columns are collapsed, gene by gene, into their distinct patterns in ascending
  * strcmp order of (character + 1), each represented by the first site showing it -- the reference's order, counts and

@@ -17,6 +17,7 @@
 #include "prune4.cuh"
 #include "prune4v2.cuh"
 #include "eigen.cuh"
+#include "cond.cuh"
 #include "plan.h"
 
 using namespace pb200;
@@ -123,6 +124,13 @@ struct pb200_ctx {
     DevBuf d_prog;
     // eval
     DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush, d_item_partial;
+    // conditional vectors resident in HBM (pb200_cond_update / pb200_branch_lnl, cond.cuh)
+    DevBuf d_cond, d_cscale, d_cstage, d_cP, d_cP3, d_cpart, d_cres, d_cbr;
+    void* h_cstage = nullptr;   // pinned mirror of d_cstage (sets | t | set | son lists)
+    size_t h_cstage_cap = 0;
+    void* h_cbr = nullptr;      // pinned: per-call inputs of pb200_branch_lnl + its 3 results
+    int cond_nclass = 0, cond_nscale = 0;
+    struct { int kind, nr, nset; long long set_stride; size_t off_sets; bool ok; } csets = {0, 0, 0, 0, 0, false};
     DevBuf d_eig;               // pb200_eigen_qrev: Q | pi | sets | info
     void* h_eig = nullptr;      // its pinned mirror
     size_t h_eig_cap = 0;
@@ -198,10 +206,13 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
                       &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs,
-                      &c->d_ops4, &c->d_tip_order, &c->d_zw, &c->d_eig};
+                      &c->d_ops4, &c->d_tip_order, &c->d_zw, &c->d_eig,
+                      &c->d_cond, &c->d_cscale, &c->d_cstage, &c->d_cP, &c->d_cP3, &c->d_cpart, &c->d_cres, &c->d_cbr};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_eig) cudaFreeHost(c->h_eig);
+    if (c->h_cstage) cudaFreeHost(c->h_cstage);
+    if (c->h_cbr) cudaFreeHost(c->h_cbr);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1064,6 +1075,8 @@ extern "C" int pb200_eigen_qrev(pb200_ctx* c, int n, int njob, const double* Q, 
     const size_t off_info = align16(off_sets + (size_t)njob * stride * 8), total = align16(off_info + (size_t)njob * 4);
     if (total > c->h_eig_cap) {
         if (c->h_eig) cudaFreeHost(c->h_eig);
+    if (c->h_cstage) cudaFreeHost(c->h_cstage);
+    if (c->h_cbr) cudaFreeHost(c->h_cbr);
         c->h_eig = nullptr; c->h_eig_cap = 0;
         CUDA_TRY(cudaMallocHost(&c->h_eig, total + total / 4));
         c->h_eig_cap = total + total / 4;
@@ -1099,6 +1112,174 @@ extern "C" int pb200_eigen_qrev(pb200_ctx* c, int n, int njob, const double* Q, 
     }
     for (int j = 0; j < njob; j++)
         if (info[j] < 0) return fail("pb200_eigen_qrev: matrix %d did not converge in %d Jacobi sweeps", j, -info[j] - 1);
+    return 0;
+}
+
+// ---- conditional vectors resident in HBM: the minbranches family (cond.cuh) ----
+extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr, int nset, long long set_stride,
+                                 const double* set_data, const int* branch_set, const double* branch_t, int nupd,
+                                 const int* upd_node, const int* upd_nson, const int* upd_sons, int maxsons,
+                                 const unsigned char* scale_flags)
+{
+    if (!c) return fail("pb200_cond_update: null context");
+    if (c->npatt == 0 || c->nnode == 0) return fail("pb200_cond_update: set_data and set_tree must be called first");
+    if (nclass < 1 || nupd < 0 || !branch_set || !branch_t || (nupd && (!upd_node || !upd_nson || !upd_sons)) || maxsons < 1)
+        return fail("pb200_cond_update: bad arguments");
+    if (check_sets(c->n, set_kind, nr, nset, set_stride)) return 1;
+    if (set_stride > 0 && !set_data) return fail("pb200_cond_update: null set_data");
+    const int n = c->n, nnode = c->nnode, ns = c->ns, nint = nnode - ns;
+    if (nint < 1) return fail("pb200_cond_update: no internal nodes");
+    int nscale = 0;
+    std::vector<int> scale_k(nnode, -1);
+    if (scale_flags)
+        for (int i = 0; i < nnode; i++) if (scale_flags[i]) scale_k[i] = nscale++;      // k-th scaling node, src/treesub.c:7207-7211
+    // every son reference must be a known node, every updated node internal, every non-tip son's branch mapped to a set
+    std::vector<unsigned char> used(nnode, 0);
+    for (int u = 0; u < nupd; u++) {
+        if (upd_node[u] < ns || upd_node[u] >= nnode) return fail("pb200_cond_update: node %d is not an internal node", upd_node[u]);
+        if (upd_nson[u] < 1 || upd_nson[u] > maxsons) return fail("pb200_cond_update: node %d has %d sons", upd_node[u], upd_nson[u]);
+        for (int s = 0; s < upd_nson[u]; s++) {
+            int son = upd_sons[u * maxsons + s];
+            if (son < 0 || son >= nnode || son == upd_node[u]) return fail("pb200_cond_update: bad son %d of node %d", son, upd_node[u]);
+            used[son] = 1;
+        }
+    }
+    const int nmat = nclass * nnode;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<int> bs(nmat);
+    for (int m = 0; m < nmat; m++) {
+        int node = m % nnode;
+        bs[m] = used[node] ? branch_set[m] : -1;             // P(t) only for the branches this call reads
+        if (used[node] && (bs[m] < 0 || bs[m] >= nset)) return fail("pb200_cond_update: branch_set[%d] = %d out of range", m, bs[m]);
+    }
+    if (c->cond_nclass != nclass || c->cond_nscale != nscale || !c->d_cond.p) {
+        if (c->d_cond.ensure((size_t)nclass * nint * c->npatt * n * 8)) return 1;
+        if (c->d_cscale.ensure((size_t)std::max(1, nclass * nscale) * c->npatt * 8)) return 1;
+        c->cond_nclass = nclass; c->cond_nscale = nscale;
+    }
+    // staging: sets | t | set | son lists
+    size_t off_sets = 0;
+    size_t off_t = align16(off_sets + (size_t)nset * set_stride * 8);
+    size_t off_set = align16(off_t + (size_t)nmat * 8);
+    size_t off_sons = align16(off_set + (size_t)nmat * 4);
+    size_t total = align16(off_sons + (size_t)std::max(1, nupd) * maxsons * 4);
+    if (total > c->h_cstage_cap) {
+        if (c->h_cstage) cudaFreeHost(c->h_cstage);
+        c->h_cstage = nullptr; c->h_cstage_cap = 0;
+        CUDA_TRY(cudaMallocHost(&c->h_cstage, total + total / 4));
+        c->h_cstage_cap = total + total / 4;
+    }
+    if (c->d_cstage.ensure(total) || c->d_cP.ensure((size_t)nmat * n * n * 8)) return 1;
+    char* hs = (char*)c->h_cstage;
+    char* ds = (char*)c->d_cstage.p;
+    if (set_stride > 0) memcpy(hs + off_sets, set_data, (size_t)nset * set_stride * 8);
+    memcpy(hs + off_t, branch_t, (size_t)nmat * 8);
+    memcpy(hs + off_set, bs.data(), (size_t)nmat * 4);
+    if (nupd) memcpy(hs + off_sons, upd_sons, (size_t)nupd * maxsons * 4);
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, c->stream));
+    c->csets.kind = set_kind; c->csets.nr = nr; c->csets.nset = nset; c->csets.set_stride = set_stride; c->csets.off_sets = off_sets;
+    c->csets.ok = true;
+    if (nupd) {
+        if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
+                      (const double*)(ds + off_t), (double*)c->d_cP.p, (long long)n * n, PT_MODE_PLAIN, nnode, ns, c->NT, c->KS, c->ncodes))
+            return 1;
+        const size_t smem = ((size_t)n * n + 2 * (size_t)COND_TP * (n | 1)) * sizeof(double);
+        static bool attr_set[64] = {false};
+        if (c->device < 64 && !attr_set[c->device]) {
+            CUDA_TRY(cudaFuncSetAttribute(cond_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 2 * COND_TP * 65) * 8));
+            CUDA_TRY(cudaFuncSetAttribute(branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (3 * 64 * 64 + 2 * COND_TP * 65 + 3 * 8 * COND_TP + COND_TP) * 8));
+            attr_set[c->device] = true;
+        }
+        for (int u = 0; u < nupd; u++) {
+            CondNodeParams p;
+            p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.nson = upd_nson[u]; p.node = upd_node[u];
+            p.scale_k = scale_k[upd_node[u]]; p.nscale = nscale; p.npatt = c->npatt; p.zstride = c->zstride;
+            p.sons = (const int*)(ds + off_sons) + (size_t)u * maxsons;
+            p.P = (const double*)c->d_cP.p; p.z = (const unsigned char*)c->d_z.p;
+            p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
+            p.cond = (double*)c->d_cond.p; p.scaleF = (double*)c->d_cscale.p;
+            dim3 grid((unsigned)((c->npatt + COND_TP - 1) / COND_TP), nclass);
+            cond_node_kernel<<<grid, COND_THREADS, smem, c->stream>>>(p);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));               // the pinned staging block is reused by the next call
+    return 0;
+}
+
+extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, int a, int b, double t, const double* mult,
+                                const int* set_of_class, const double* pi, int semantics, int want_dd, double out[3])
+{
+    if (!c || !mult || !set_of_class || !pi || !out) return fail("pb200_branch_lnl: null argument");
+    if (!c->d_cond.p || c->cond_nclass != nclass || !c->csets.ok) return fail("pb200_branch_lnl: pb200_cond_update must come first (same nclass)");
+    if (c->csets.kind != KIND_UVROOT && c->csets.kind != KIND_CIJK) return fail("pb200_branch_lnl: needs UVROOT or CIJK spectral sets");
+    if (semantics != BR_SEM_LFUNT && semantics != BR_SEM_SITECLASS) return fail("pb200_branch_lnl: bad semantics");
+    if (semantics == BR_SEM_SITECLASS && !freqK) return fail("pb200_branch_lnl: null freqK");
+    const int n = c->n, nnode = c->nnode, ns = c->ns;
+    if (a < ns || a >= nnode || b < 0 || b >= nnode || a == b) return fail("pb200_branch_lnl: bad branch %d..%d", a, b);
+    for (int k = 0; k < nclass; k++)
+        if (set_of_class[k] < 0 || set_of_class[k] >= c->csets.nset) return fail("pb200_branch_lnl: set_of_class[%d] out of range", k);
+    CUDA_TRY(cudaSetDevice(c->device));
+    // per-call inputs: freqK | mult | pi | set_of_class ; results: 3 doubles
+    size_t off_f = 0, off_m = align16(off_f + (size_t)nclass * 8), off_pi = align16(off_m + (size_t)nclass * 8);
+    size_t off_s = align16(off_pi + (size_t)n * 8), off_r = align16(off_s + (size_t)nclass * 4), total = off_r + 32;
+    if (!c->h_cbr) CUDA_TRY(cudaMallocHost(&c->h_cbr, 1 << 16));
+    if (total > (1 << 16)) return fail("pb200_branch_lnl: too many classes");
+    const int nblk = (int)((c->npatt + COND_TP - 1) / COND_TP);
+    if (c->d_cbr.ensure(total) || c->d_cP3.ensure((size_t)nclass * 3 * n * n * 8) || c->d_cpart.ensure((size_t)nblk * 3 * 8) || c->d_cres.ensure(32))
+        return 1;
+    char* hs = (char*)c->h_cbr;
+    char* ds = (char*)c->d_cbr.p;
+    for (int k = 0; k < nclass; k++) ((double*)(hs + off_f))[k] = freqK ? freqK[k] : 1.0;
+    memcpy(hs + off_m, mult, (size_t)nclass * 8);
+    memcpy(hs + off_pi, pi, (size_t)n * 8);
+    memcpy(hs + off_s, set_of_class, (size_t)nclass * 4);
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, off_r, cudaMemcpyHostToDevice, c->stream));
+    Pt3Params q;
+    q.n = n; q.kind = c->csets.kind; q.nr = c->csets.nr; q.nclass = nclass; q.set_stride = c->csets.set_stride;
+    q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + off_s);
+    q.mult = (const double*)(ds + off_m); q.t = t; q.out = (double*)c->d_cP3.p;
+    pt3_kernel<<<nclass, 256, 0, c->stream>>>(q);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    BranchParams p;
+    p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.a = a; p.b = b; p.nscale = c->cond_nscale;
+    p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride;
+    p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
+    p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
+    p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
+    p.partial = (double*)c->d_cpart.p;
+    const size_t smem = (3 * (size_t)n * n + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + COND_TP) * sizeof(double);
+    branch_kernel<<<nblk, COND_THREADS, smem, c->stream>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    cond_sum_kernel<<<1, 256, 0, c->stream>>>((const double*)c->d_cpart.p, nblk, (double*)c->d_cres.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(hs + off_r, c->d_cres.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out, hs + off_r, 24);
+    return 0;
+}
+
+// Test / inspection: the resident conditional vectors of one internal node, [nclass][npatt][n], and the scale factors
+// [nclass][nscale][npatt] (either may be NULL).
+extern "C" int pb200_cond_get(pb200_ctx* c, int node, double* cond, double* scaleF)
+{
+    if (!c) return fail("pb200_cond_get: null context");
+    if (!c->d_cond.p || c->cond_nclass < 1) return fail("pb200_cond_get: nothing resident");
+    if (node < c->ns || node >= c->nnode) return fail("pb200_cond_get: node %d is not internal", node);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t per = (size_t)c->npatt * c->n, nint = (size_t)(c->nnode - c->ns);
+    if (cond)
+        for (int k = 0; k < c->cond_nclass; k++)
+            CUDA_TRY(cudaMemcpyAsync(cond + k * per, (const double*)c->d_cond.p + ((size_t)k * nint + (node - c->ns)) * per, per * 8,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    if (scaleF && c->cond_nscale)
+        CUDA_TRY(cudaMemcpyAsync(scaleF, c->d_cscale.p, (size_t)c->cond_nclass * c->cond_nscale * c->npatt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

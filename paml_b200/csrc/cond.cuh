@@ -1,0 +1,335 @@
+// cond.cuh -- conditional-likelihood vectors RESIDENT in HBM, for the one-branch-at-a-time optimiser.
+//
+// The evaluation kernels (kernels.cuh, prune4v2.cuh) never materialise internal-node vectors.  minbranches
+// (src/treesub.c:8039-8123, `method = 1`) needs them: it reroots the tree at every branch b->a in turn, refreshes only
+// the vectors on the path between two consecutive roots (ReRootTree src/treespace.c:236, updateconP src/treesub.c:7982,
+// ConditionalPNode src/codeml.c:3526 with com.oldconP), and runs Newton steps on that branch's length from
+// f_h(t) = sum_i pi_i L_b(i) sum_j P_ij(t) L_a(j) and its first two derivatives (lfunt / lfuntdd and their _SiteClass
+// forms, src/treesub.c:8127-8543).  Here:
+//   cond_node_kernel   one internal node: L[h][j] = prod_sons sum_k P_son[j][k] L_son[h][k]  (tips: column / ambiguity
+//                      sums of P), optional NodeScale (src/treesub.c:7200-7230); reads the sons' vectors from HBM, writes
+//                      the node's -- layout [class][internal node][pattern][state], the reference's own.
+//   pt3_kernel         P, dP/dt, d2P/dt2 of the branch under the Newton iteration, per site class, from the spectral set
+//                      exactly as lfuntdd forms them (no expm1, root 0 skipped in the derivatives).
+//   branch_kernel      per pattern f, f', f'' summed over site classes (with the per-class scale bookkeeping of
+//                      lfuntdd_SiteClass), then -sum fpatt log f etc.; deterministic block partials + cond_sum_kernel.
+// These are streaming kernels on the FP64 vector pipe (2 n^2 flops per pattern and son against 16 n bytes): at n = 61
+// compute-bound, at n = 4 HBM-bound.  First correct version: plain shared-memory tiles, no DMMA yet.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pb200 {
+
+constexpr int COND_TP = 32;          // patterns per block (one per lane)
+constexpr int COND_THREADS = 256;    // 8 warps: warp w owns the states / rows  w, w+8, w+16, ...
+
+struct CondNodeParams {
+    int n, nclass, nnode, ns, ncodes, nson, node, scale_k, nscale;
+    long long npatt, zstride;
+    const int* sons;                 // [nson] node ids (device)
+    const double* P;                 // [nclass][nnode][n*n] plain row-major P(t) of every branch (by child node)
+    const unsigned char* z;          // [ns][zstride] compact codes
+    const unsigned char* amb_n;      // [ncodes - n]
+    const unsigned char* amb_map;    // [ncodes - n][64]
+    double* cond;                    // [nclass][nnode - ns][npatt][n]
+    double* scaleF;                  // [nclass][nscale][npatt]
+};
+
+__global__ void __launch_bounds__(COND_THREADS) cond_node_kernel(const CondNodeParams p)
+{
+    extern __shared__ __align__(16) double csm[];
+    const int n = p.n, LDT = n | 1;
+    double* Ps = csm;                          // [n][n]
+    double* tin = Ps + n * n;                  // [TP][LDT] a son's vectors
+    double* tout = tin + COND_TP * LDT;        // [TP][LDT] this node's vectors
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, cls = blockIdx.y;
+    const long long h0 = (long long)blockIdx.x * COND_TP, h = h0 + lane;
+    const int nh = (int)min((long long)COND_TP, p.npatt - h0);
+    const bool valid = lane < nh;
+    const size_t nint = (size_t)(p.nnode - p.ns);
+    double* cbase = p.cond + (size_t)cls * nint * p.npatt * n;
+
+    double acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) acc[jj] = 1.0;             // src/codeml.c:3539-3540
+
+    for (int s = 0; s < p.nson; s++) {
+        const int son = p.sons[s];
+        const double* Pm = p.P + ((size_t)cls * p.nnode + son) * n * n;
+        __syncthreads();                                        // previous son's tiles fully consumed
+        for (int e = tid; e < n * n; e += COND_THREADS) Ps[e] = Pm[e];
+        if (son >= p.ns) {
+            const double* src = cbase + ((size_t)(son - p.ns) * p.npatt + h0) * n;
+            for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tin[hh * LDT + k] = src[e]; }
+        }
+        __syncthreads();
+        if (valid) {
+            if (son < p.ns) {                                   // tip: src/codeml.c:3555-3567
+                const int code = p.z[(size_t)son * p.zstride + h];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int j = w + 8 * jj;
+                    if (j < n) {
+                        double t;
+                        if (code < n) t = Ps[j * n + code];
+                        else {
+                            const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
+                            const int cnt = p.amb_n[code - n];
+                            t = 0.0;
+                            for (int k = 0; k < cnt; k++) t = __dadd_rn(t, Ps[j * n + mp[k]]);
+                        }
+                        acc[jj] = __dmul_rn(acc[jj], t);
+                    }
+                }
+            }
+            else {                                              // internal son: src/codeml.c:3568-3575
+                const double* v = tin + lane * LDT;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int j = w + 8 * jj;
+                    if (j < n) {
+                        const double* pr = Ps + j * n;
+                        double t = 0.0;
+                        for (int k = 0; k < n; k++) t = __dadd_rn(t, __dmul_rn(pr[k], v[k]));
+                        acc[jj] = __dmul_rn(acc[jj], t);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) { const int j = w + 8 * jj; if (j < n) tout[lane * LDT + j] = acc[jj]; }
+    }
+    __syncthreads();
+    if (p.scale_k >= 0) {                                       // NodeScale, src/treesub.c:7214-7228
+        if (tid < nh) {
+            double* v = tout + tid * LDT;
+            double t = 0.0;
+            for (int j = 0; j < n; j++) if (v[j] > t) t = v[j];
+            double f;
+            if (t < 1e-300) { for (int j = 0; j < n; j++) v[j] = 1.0; f = -800.0; }
+            else { for (int j = 0; j < n; j++) v[j] = v[j] / t; f = log(t); }
+            p.scaleF[((size_t)cls * p.nscale + p.scale_k) * p.npatt + h0 + tid] = f;
+        }
+        __syncthreads();
+    }
+    double* dst = cbase + ((size_t)(p.node - p.ns) * p.npatt + h0) * n;
+    for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; dst[e] = tout[hh * LDT + k]; }
+}
+
+// ---- P, P', P'' of the branch being optimised ----
+struct Pt3Params {
+    int n, kind, nr, nclass;
+    long long set_stride;
+    const double* sets;       // resident spectral sets
+    const int* set_of_class;  // [nclass]
+    const double* mult;       // [nclass] rgene * _rateSite * Qfactor (src/treesub.c:8435-8439)
+    double t;
+    double* out;              // [nclass][3][n*n]
+};
+
+__global__ void __launch_bounds__(256) pt3_kernel(const Pt3Params p)
+{
+    __shared__ double ex[64], mu[64];
+    const int n = p.n, cls = blockIdx.x, tid = threadIdx.x;
+    const double* set = p.sets + (size_t)p.set_of_class[cls] * p.set_stride;
+    const int nroot = (p.kind == KIND_UVROOT) ? n : p.nr;
+    const double* Root = set;
+    if (tid < nroot) {
+        const double m = __dmul_rn(p.mult[cls], Root[tid]);     // "multiply", src/treesub.c:8266
+        mu[tid] = m;
+        ex[tid] = tid ? exp(__dmul_rn(p.t, m)) : 1.0;           // expt = 1 for the first root (src/treesub.c:8265-8267)
+    }
+    __syncthreads();
+    double* o = p.out + (size_t)cls * 3 * n * n;
+    for (int e = tid; e < n * n; e += 256) {
+        const int i = e / n, j = e - i * n;
+        double P = 0.0, dP = 0.0, ddP = 0.0;
+        if (p.kind == KIND_UVROOT) {
+            const double *U = set + n, *V = set + n + (size_t)n * n;
+            for (int k = 0; k < nroot; k++) {
+                const double uv = __dmul_rn(__dmul_rn(U[i * n + k], ex[k]), V[k * n + j]);   // uexpt * V[k][j]
+                P = __dadd_rn(P, uv);
+                if (k) {
+                    const double d1 = __dmul_rn(uv, mu[k]);
+                    dP = __dadd_rn(dP, d1);
+                    ddP = __dadd_rn(ddP, __dmul_rn(d1, mu[k]));
+                }
+            }
+        }
+        else {                                                  // Cijk form, src/treesub.c:8280-8287
+            const double* C = set + p.nr + ((size_t)i * n + j) * p.nr;
+            for (int k = 0; k < nroot; k++) {
+                const double ce = __dmul_rn(C[k], ex[k]);
+                P = __dadd_rn(P, ce);
+                if (k) {
+                    const double d1 = __dmul_rn(ce, mu[k]);
+                    dP = __dadd_rn(dP, d1);
+                    ddP = __dadd_rn(ddP, __dmul_rn(d1, mu[k]));
+                }
+            }
+        }
+        o[e] = P; o[n * n + e] = dP; o[2 * n * n + e] = ddP;
+    }
+}
+
+// ---- f, f', f'' per pattern, summed over classes; -lnL and its two derivatives in t ----
+enum { BR_SEM_LFUNT = 0, BR_SEM_SITECLASS = 1 };
+
+struct BranchParams {
+    int n, nclass, nnode, ns, ncodes, a, b, nscale, semantics, want_dd;
+    long long npatt, zstride;
+    const double* P3;          // [nclass][3][n*n]
+    const double* cond;        // [nclass][nint][npatt][n]
+    const double* scaleF;      // [nclass][nscale][npatt]
+    const double* freqK;       // [nclass]
+    const double* pi;          // [n]
+    const double* fpatt;       // [npatt]
+    const unsigned char* z;
+    const unsigned char* amb_n;
+    const unsigned char* amb_map;
+    double* partial;           // [gridDim.x][3]
+};
+
+__global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams p)
+{
+    extern __shared__ __align__(16) double bsm[];
+    const int n = p.n, LDT = n | 1, nm = p.want_dd ? 3 : 1;
+    double* P3 = bsm;                           // [3][n][n]
+    double* tA = P3 + 3 * n * n;                // [TP][LDT]
+    double* tB = tA + COND_TP * LDT;            // [TP][LDT]
+    double* red = tB + COND_TP * LDT;           // [3][8][TP]
+    double* Sh = red + 3 * 8 * COND_TP;         // [TP]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long h0 = (long long)blockIdx.x * COND_TP, h = h0 + lane;
+    const int nh = (int)min((long long)COND_TP, p.npatt - h0);
+    const bool valid = lane < nh;
+    const size_t nint = (size_t)(p.nnode - p.ns);
+    const bool btip = p.b < p.ns;
+
+    // scale bookkeeping of lfuntdd_SiteClass (src/treesub.c:8437-8449): Sh = largest per-class sum of scale factors
+    if (tid < COND_TP) {
+        double best = 0.0;
+        if (p.nscale > 0 && tid < nh) {
+            for (int ir = 0; ir < p.nclass; ir++) {
+                double y = 0.0;
+                for (int k = 0; k < p.nscale; k++) y += p.scaleF[((size_t)ir * p.nscale + k) * p.npatt + h0 + tid];
+                if (ir == 0 || y > best) best = y;
+            }
+        }
+        Sh[tid] = best;
+    }
+    double fh = 0.0, dfh = 0.0, ddfh = 0.0;      // lanes of warp 0 accumulate over the classes
+    for (int cls = 0; cls < p.nclass; cls++) {
+        __syncthreads();
+        const double* Pm = p.P3 + (size_t)cls * 3 * n * n;
+        for (int e = tid; e < nm * n * n; e += COND_THREADS) P3[e] = Pm[e];
+        const double* cb = p.cond + (size_t)cls * nint * p.npatt * n;
+        {
+            const double* src = cb + ((size_t)(p.a - p.ns) * p.npatt + h0) * n;
+            for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tA[hh * LDT + k] = src[e]; }
+        }
+        if (!btip) {
+            const double* src = cb + ((size_t)(p.b - p.ns) * p.npatt + h0) * n;
+            for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tB[hh * LDT + k] = src[e]; }
+        }
+        __syncthreads();
+        double f = 0.0, df = 0.0, ddf = 0.0;
+        if (valid) {
+            double pK = 1.0;
+            if (p.semantics == BR_SEM_SITECLASS) {
+                pK = p.freqK[cls];
+                if (p.nscale > 0) {
+                    double y = 0.0;
+                    for (int k = 0; k < p.nscale; k++) y += p.scaleF[((size_t)cls * p.nscale + k) * p.npatt + h];
+                    pK = pK * exp(y - Sh[lane]);
+                }
+            }
+            const double* va = tA + lane * LDT;
+            int n1 = n, code = 0;
+            const unsigned char* mp = nullptr;
+            if (btip) {
+                code = p.z[(size_t)p.b * p.zstride + h];
+                if (code < n) n1 = 1;
+                else { n1 = p.amb_n[code - n]; mp = p.amb_map + (size_t)(code - n) * 64; }
+            }
+            for (int ii = w; ii < n1; ii += 8) {                // rows of P shared out over the 8 warps
+                int xb = ii;
+                double piqi;
+                if (btip) { xb = (code < n) ? code : mp[ii]; piqi = pK * p.pi[xb]; }
+                else piqi = pK * p.pi[ii] * tB[lane * LDT + ii];
+                const double* pr = P3 + xb * n;
+                double pq = 0.0, dpq = 0.0, ddpq = 0.0;
+                if (p.want_dd) {
+                    const double *dr = pr + n * n, *ddr = dr + n * n;
+                    for (int j = 0; j < n; j++) {
+                        const double aj = va[j];
+                        pq = __dadd_rn(pq, __dmul_rn(pr[j], aj));
+                        dpq = __dadd_rn(dpq, __dmul_rn(dr[j], aj));
+                        ddpq = __dadd_rn(ddpq, __dmul_rn(ddr[j], aj));
+                    }
+                }
+                else
+                    for (int j = 0; j < n; j++) pq = __dadd_rn(pq, __dmul_rn(pr[j], va[j]));
+                f += piqi * pq; df += piqi * dpq; ddf += piqi * ddpq;
+            }
+        }
+        red[(0 * 8 + w) * COND_TP + lane] = f;
+        red[(1 * 8 + w) * COND_TP + lane] = df;
+        red[(2 * 8 + w) * COND_TP + lane] = ddf;
+        __syncthreads();
+        if (w == 0) {
+            for (int ww = 0; ww < 8; ww++) {
+                fh += red[(0 * 8 + ww) * COND_TP + lane];
+                dfh += red[(1 * 8 + ww) * COND_TP + lane];
+                ddfh += red[(2 * 8 + ww) * COND_TP + lane];
+            }
+        }
+    }
+    if (w == 0) {
+        double l = 0.0, dl = 0.0, ddl = 0.0;
+        if (valid) {
+            const double fp = p.fpatt[h];
+            if (fp != 0.0) {
+                const double lf = (p.semantics == BR_SEM_LFUNT && !p.want_dd && fh < 0) ? -500.0 : log(fh);   // src/treesub.c:8192-8193
+                l = -(lf * fp);
+                if (p.nscale > 0) l -= Sh[lane] * fp;
+                if (p.want_dd) {
+                    dl = -(dfh / fh * fp);
+                    ddl = -((fh * ddfh - dfh * dfh) / (fh * fh) * fp);
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {                      // fixed-order tree: the sums are reproducible call to call
+            l += __shfl_down_sync(0xffffffffu, l, o);
+            dl += __shfl_down_sync(0xffffffffu, dl, o);
+            ddl += __shfl_down_sync(0xffffffffu, ddl, o);
+        }
+        if (lane == 0) {
+            p.partial[(size_t)blockIdx.x * 3 + 0] = l;
+            p.partial[(size_t)blockIdx.x * 3 + 1] = dl;
+            p.partial[(size_t)blockIdx.x * 3 + 2] = ddl;
+        }
+    }
+}
+
+// fixed-order sum of the block partials: out[3]
+__global__ void __launch_bounds__(256) cond_sum_kernel(const double* partial, int nblk, double* out)
+{
+    __shared__ double s[3][256];
+    const int tid = threadIdx.x;
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < nblk; i += 256)
+        for (int m = 0; m < 3; m++) a[m] += partial[(size_t)i * 3 + m];
+    for (int m = 0; m < 3; m++) s[m][tid] = a[m];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) for (int m = 0; m < 3; m++) s[m][tid] += s[m][tid + o];
+        __syncthreads();
+    }
+    if (tid < 3) out[tid] = s[tid][0];
+}
+
+}  // namespace pb200

@@ -156,6 +156,48 @@ class TreeLikelihood:
                                  _ptr(mat_set, C.c_int), _ptr(mat_t, C.c_double), _ptr(out, C.c_double)))
         return out
 
+    # -- conditional vectors resident in HBM (minbranches family) ---------------------------------------
+    def cond_update(self, set_kind, nr, set_data, branch_set, branch_t, updates, scale_flags=None):
+        """pb200_cond_update.  updates: list of (node, [sons]) in the order to compute (sons before fathers)."""
+        set_data = np.ascontiguousarray(set_data, np.float64)
+        if set_data.ndim == 1:
+            set_data = set_data.reshape(1, -1)
+        branch_set = np.ascontiguousarray(branch_set, np.int32)
+        branch_t = np.ascontiguousarray(branch_t, np.float64)
+        nclass = branch_set.shape[0]
+        maxsons = max([len(sn) for _, sn in updates] + [1])
+        un = np.array([u for u, _ in updates], np.int32)
+        uc = np.array([len(sn) for _, sn in updates], np.int32)
+        us = np.full((max(1, len(updates)), maxsons), -1, np.int32)
+        for i, (_, sn) in enumerate(updates):
+            us[i, :len(sn)] = sn
+        flags = None if scale_flags is None else np.ascontiguousarray(scale_flags, np.uint8)
+        check(self._L.pb200_cond_update(self._ctx, C.c_int(nclass), C.c_int(set_kind), C.c_int(nr), C.c_int(set_data.shape[0]),
+                                        C.c_longlong(set_data.shape[1]), _ptr(set_data, C.c_double), _ptr(branch_set, C.c_int),
+                                        _ptr(branch_t, C.c_double), C.c_int(len(updates)), _ptr(un, C.c_int), _ptr(uc, C.c_int),
+                                        _ptr(us, C.c_int), C.c_int(maxsons), _ptr(flags, C.c_ubyte)))
+        self.cond_nclass = nclass
+        self.cond_nscale = 0 if flags is None else int(flags.astype(bool).sum())
+
+    def branch_lnl(self, freqK, a, b, t, mult, set_of_class, pi, semantics, want_dd=True):
+        """pb200_branch_lnl -> (-lnL, d/dt, d2/dt2) for the branch b -> a at length t."""
+        mult = np.ascontiguousarray(mult, np.float64)
+        soc = np.ascontiguousarray(set_of_class, np.int32)
+        pi = np.ascontiguousarray(pi, np.float64)
+        fk = None if freqK is None else np.ascontiguousarray(freqK, np.float64)
+        out = np.zeros(3)
+        check(self._L.pb200_branch_lnl(self._ctx, C.c_int(mult.shape[0]), _ptr(fk, C.c_double), C.c_int(a), C.c_int(b),
+                                       C.c_double(float(t)), _ptr(mult, C.c_double), _ptr(soc, C.c_int), _ptr(pi, C.c_double),
+                                       C.c_int(semantics), C.c_int(1 if want_dd else 0), _ptr(out, C.c_double)))
+        return out
+
+    def cond_get(self, node):
+        """Resident vectors of one internal node [nclass, npatt, n] and the scale factors [nclass, nscale, npatt]."""
+        cond = np.zeros((self.cond_nclass, self.npatt, self.n))
+        sc = np.zeros((self.cond_nclass, max(1, self.cond_nscale), self.npatt))
+        check(self._L.pb200_cond_get(self._ctx, C.c_int(node), _ptr(cond, C.c_double), _ptr(sc, C.c_double)))
+        return cond, sc[:, :self.cond_nscale]
+
     def eigen_qrev(self, Q, pi):
         """pb200_eigen_qrev: Q [njob, n, n] (or [n, n]), pi [njob, n] -> Root [njob, n], U, V [njob, n, n], sweeps [njob]."""
         Q = np.ascontiguousarray(Q, np.float64)
