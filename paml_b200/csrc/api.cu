@@ -291,6 +291,7 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
         c->zw_dirty = true;
     }
     c->have_eval = false;
+    c->cond_nclass = 0; c->csets.ok = false;             // resident conditional vectors belong to the old data
     return 0;
 }
 
@@ -372,6 +373,7 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
         c->zw_dirty = true;
     }
     static unsigned long long gen_counter = 0;
+    if (nnode != c->nnode) { c->cond_nclass = 0; c->csets.ok = false; }   // resident conditional vectors are laid out per node
     c->plan = pl; c->nnode = nnode; c->root = root; c->plan_gen = ++gen_counter;
     c->have_eval = false;
     return 0;
@@ -1152,11 +1154,10 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
         bs[m] = used[node] ? branch_set[m] : -1;             // P(t) only for the branches this call reads
         if (used[node] && (bs[m] < 0 || bs[m] >= nset)) return fail("pb200_cond_update: branch_set[%d] = %d out of range", m, bs[m]);
     }
-    if (c->cond_nclass != nclass || c->cond_nscale != nscale || !c->d_cond.p) {
-        if (c->d_cond.ensure((size_t)nclass * nint * c->npatt * n * 8)) return 1;
-        if (c->d_cscale.ensure((size_t)std::max(1, nclass * nscale) * c->npatt * 8)) return 1;
-        c->cond_nclass = nclass; c->cond_nscale = nscale;
-    }
+    // (a change of nclass / nscale / data / tree re-lays the store out: the caller recomputes every node it needs)
+    if (c->d_cond.ensure((size_t)nclass * nint * c->npatt * n * 8)) return 1;
+    if (c->d_cscale.ensure((size_t)std::max(1, nclass * nscale) * c->npatt * 8)) return 1;
+    c->cond_nclass = nclass; c->cond_nscale = nscale;
     // staging: sets | t | set | son lists
     size_t off_sets = 0;
     size_t off_t = align16(off_sets + (size_t)nset * set_stride * 8);

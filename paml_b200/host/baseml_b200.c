@@ -9,12 +9,22 @@
  *   PatternWeight   (the step upstream of the path) the same way: `PatternWeight(void)` -> PatternWeight_ref, the call
  *                   `PatternWeight()` -> PatternWeight_b200;
  *   eigenQREV       lives in tools.c (a separate object): only the CALLS made from this translation unit are renamed, to
- *                   eigenQREV_b200 (device Jacobi for codon-sized matrices), which can still call the original. */
+ *                   eigenQREV_b200 (device Jacobi for codon-sized matrices), which can still call the original;
+ *   minbranches, updateconP, lfunt, lfuntdd, lfunt_SiteClass, lfuntdd_SiteClass   (`method = 1`) by the same first-argument
+ *                   rule: the reference's minbranches keeps its control flow (as minbranches_ref) while the data-touching
+ *                   calls inside it go to conditional vectors resident in HBM. */
 double lfun(double x[], int np);
 double lfundG(double x[], int np);
 int fx_r_gpu(double x[], int np);
 int PatternWeight_b200(void);
 int eigenQREV_b200(double Q[], double pi[], int n, double Root[], double U[], double V[], double spacesqrtpi[]);
+int updateconP_disp(double x[], int inode);
+double minbranches_b200(double xcom[], int np);
+double minbranches(double xcom[], int np);     /* the bare name (passed to ming2 in minB2, src/treesub.c:7968) is ours too */
+int lfunt_disp(double t, int a, int b, double xcom[], double *l, double space[]);
+int lfuntdd_disp(double t, int a, int b, double xcom[], double *l, double *dl, double *ddl, double space[]);
+int lfunt_SiteClass_disp(double t, int a, int b, double xcom[], double *l, double space[]);
+int lfuntdd_SiteClass_disp(double t, int a, int b, double xcom[], double *l, double *dl, double *ddl, double space[]);
 #define lfun(a, b)   lfun_ref(a, b)
 #define lfundG(a, b) lfundG_ref(a, b)
 #define fx_r(a, b)   PBH_FXR_##a, b)
@@ -22,6 +32,25 @@ int eigenQREV_b200(double Q[], double pi[], int n, double Root[], double U[], do
 #define PBH_FXR_double fx_r_ref(double
 #define PatternWeight(a) PBH_PW_##a
 #define eigenQREV(a, b, c, d, e, f, g) eigenQREV_b200(a, b, c, d, e, f, g)
+/* method = 1: minbranches(xcom, ..), updateconP(x, ..), lfunt*(t, ..) calls -> ours; the definitions -> *_ref */
+#define minbranches(a, b) PBH_MB_##a, b)
+#define PBH_MB_xcom   minbranches_b200(xcom
+#define PBH_MB_double minbranches_ref(double
+#define updateconP(a, b) PBH_UC_##a, b)
+#define PBH_UC_x      updateconP_disp(x
+#define PBH_UC_double updateconP_ref(double
+#define lfunt(a, b, c, d, e, f) PBH_LT_##a, b, c, d, e, f)
+#define PBH_LT_t      lfunt_disp(t
+#define PBH_LT_double lfunt_ref(double
+#define lfuntdd(a, b, c, d, e, f, g, h) PBH_LD_##a, b, c, d, e, f, g, h)
+#define PBH_LD_t      lfuntdd_disp(t
+#define PBH_LD_double lfuntdd_ref(double
+#define lfunt_SiteClass(a, b, c, d, e, f) PBH_LTS_##a, b, c, d, e, f)
+#define PBH_LTS_t      lfunt_SiteClass_disp(t
+#define PBH_LTS_double lfunt_SiteClass_ref(double
+#define lfuntdd_SiteClass(a, b, c, d, e, f, g, h) PBH_LDS_##a, b, c, d, e, f, g, h)
+#define PBH_LDS_t      lfuntdd_SiteClass_disp(t
+#define PBH_LDS_double lfuntdd_SiteClass_ref(double
 #define PBH_PW_void PatternWeight_ref(void)
 #define PBH_PW_     PatternWeight_b200()
 #include "baseml.c"
@@ -30,4 +59,10 @@ int eigenQREV_b200(double Q[], double pi[], int n, double Root[], double U[], do
 #undef fx_r
 #undef PatternWeight
 #undef eigenQREV
+#undef minbranches
+#undef updateconP
+#undef lfunt
+#undef lfuntdd
+#undef lfunt_SiteClass
+#undef lfuntdd_SiteClass
 #include "plfun_b200.inc"

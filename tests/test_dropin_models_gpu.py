@@ -196,6 +196,61 @@ def test_codeml_m2a_neb_beb_fixed_point(tmp_path):
     assert not bad, bad[:10]
 
 
+# ---- method = 1: minbranches on conditional vectors resident in HBM ----
+
+def _verbose_says_gpu(d, exe):
+    """With PB200_VERBOSE the shim reports when minbranches stays on the reference's CPU routines: it must not."""
+    r = subprocess.run([exe, "run.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=900, env=dict(os.environ, PB200_VERBOSE="1"))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "minbranches stays on the reference" not in r.stdout
+
+
+def test_method1_codeml_m0(tmp_path):
+    p = simulate.codon_m0_problem(ns=8, npatt=300, seed=71)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
+    res = _both(tmp_path, "codeml", write, "mlc")
+    _close(res, 2e-6)
+    _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "codeml_b200"))
+
+
+def test_method1_codeml_m2a_site_classes(tmp_path):
+    """NSsites = 2 with method = 1: lfunt_SiteClass / lfuntdd_SiteClass, vectors per site class."""
+    p = simulate.codon_sites_problem(ns=7, npatt=150, seed=42)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", NSsites=2, kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, ncatG=3, method=1))
+    _close(_both(tmp_path, "codeml", write, "mlc"), 2e-6)
+
+
+def test_method1_baseml_hky_gamma(tmp_path):
+    p = simulate.nuc_gtr_gamma_problem(ns=12, npatt=600, seed=23, K=4)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        with open(d + "/run.ctl", "w") as f:
+            f.write((BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=0, alpha="0.5", ncatG=4, nhomo=0, more=""))
+                    .replace("method = 0", "method = 1"))
+    _close(_both(tmp_path, "baseml", write, "mlb"), 2e-6)
+
+
+def test_method1_codeml_40_taxa_with_scaling_nodes(tmp_path):
+    """40 taxa: the reference scales at nodes with more than 15 tips below (NodeScale); rerooting moves those nodes around."""
+    p = simulate.codon_m0_problem(ns=40, npatt=150, seed=72)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
+    _close(_both(tmp_path, "codeml", write, "mlc"), 2e-6)
+
+
 def test_too_many_genes_fails_loudly(tmp_path):
     """No CPU fallback: what the GPU path does not implement stops the program with a message naming it."""
     exe = os.path.join(BIN, "baseml_b200")
