@@ -57,7 +57,7 @@ def _both(tmp_path, prog, write, outfile):
     res = {}
     for tag, exe in _pair(prog):
         d = tmp_path / tag
-        d.mkdir()
+        d.mkdir(parents=True)
         write(str(d))
         _run(exe, str(d))
         res[tag] = (_lnl(str(d / outfile)), str(d))
@@ -249,6 +249,54 @@ def test_method1_codeml_40_taxa_with_scaling_nodes(tmp_path):
         paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
                                  extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
     _close(_both(tmp_path, "codeml", write, "mlc"), 2e-6)
+
+
+def test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path):
+    """Where minbranches is NOT mapped to the GPU (here K80: closed-form P(t), no spectral set; and PB200_MINB=0) the
+    reference's CPU routines run on nodes[].conP, which the GPU likelihood never fills: the shim refreshes them with the
+    reference's own CPU evaluation first.  (Without that the fit converges to a wrong optimum.)"""
+    p = simulate.nuc_gtr_gamma_problem(ns=8, npatt=300, seed=26, K=1)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        with open(d + "/run.ctl", "w") as f:
+            f.write((BASEML_CTL % dict(Mgene=0, Malpha=0, model=1, fix_alpha=1, alpha="0", ncatG=1, nhomo=0, more=""))
+                    .replace("method = 0", "method = 1"))
+    _close(_both(tmp_path / "k80", "baseml", write, "mlb"), 2e-6)
+
+    q = simulate.codon_m0_problem(ns=8, npatt=300, seed=71)
+    ref = None
+    for tag, exe, env in (("ref", os.path.join(REF, "codeml"), {}), ("cpu_minb", os.path.join(BIN, "codeml_b200"), {"PB200_MINB": "0"})):
+        d = tmp_path / tag
+        d.mkdir()
+        paml_io.write_pattern_files(q, str(d / "s"))
+        paml_io.write_codeml_ctl(str(d / "run.ctl"), "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
+        r = subprocess.run([exe, "run.ctl"], cwd=str(d), stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=900, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout[-2000:]
+        v = _lnl(str(d / "mlc"))
+        if ref is None:
+            ref = v
+        assert abs(v - ref) <= 2e-6 * abs(ref), (tag, v, ref)
+
+
+def test_method1_ancestral_reconstruction_with_site_classes(tmp_path):
+    """RateAncestor = 1 under method = 1 with gamma rates: PostProbNode (src/treesub.c:6217-6220) reroots and calls updateconP
+    on the HOST vectors; the marginal reconstruction in `rst` must agree with the reference's."""
+    p = simulate.nuc_gtr_gamma_problem(ns=8, npatt=300, seed=25, K=4)
+
+    def write(d):
+        paml_io.write_sequence_files(p, d + "/s")
+        with open(d + "/run.ctl", "w") as f:
+            f.write((BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=0, alpha="0.5", ncatG=4, nhomo=0, more=""))
+                    .replace("method = 0", "method = 1").replace("RateAncestor = 0", "RateAncestor = 1"))
+    res = _both(tmp_path, "baseml", write, "mlb")
+    _close(res, 2e-6)
+    g, r = _numbers(res["gpu"][1] + "/rst"), _numbers(res["ref"][1] + "/rst")
+    assert len(g) == len(r) and len(r) > 500, (len(g), len(r))
+    bad = [(a, b) for (a, da), (b, db) in zip(g, r) if abs(a - b) > 2e-3 + 2.5 * 10.0 ** (-min(da, db))]
+    assert not bad, bad[:10]
 
 
 def test_too_many_genes_fails_loudly(tmp_path):
