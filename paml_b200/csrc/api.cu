@@ -1182,9 +1182,9 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
     c->csets.ok = true;
     if (nupd) {
         if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
-                      (const double*)(ds + off_t), (double*)c->d_cP.p, (long long)n * n, PT_MODE_PLAIN, nnode, ns, c->NT, c->KS, c->ncodes))
+                      (const double*)(ds + off_t), (double*)c->d_cP.p, (long long)n * n, PT_MODE_PLAIN_T, nnode, ns, c->NT, c->KS, c->ncodes))
             return 1;
-        const size_t smem = ((size_t)n * n + 2 * (size_t)COND_TP * (n | 1)) * sizeof(double);
+        const size_t smem = ((size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1)) * sizeof(double);
         static bool attr_set[64] = {false};
         if (c->device < 64 && !attr_set[c->device]) {
             CUDA_TRY(cudaFuncSetAttribute(cond_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 2 * COND_TP * 65) * 8));
@@ -1252,7 +1252,7 @@ extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, i
     p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
     p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
     p.partial = (double*)c->d_cpart.p;
-    const size_t smem = (3 * (size_t)n * n + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + COND_TP) * sizeof(double);
+    const size_t smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + COND_TP) * sizeof(double);
     branch_kernel<<<nblk, COND_THREADS, smem, c->stream>>>(p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());

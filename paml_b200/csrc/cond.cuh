@@ -14,20 +14,23 @@
 //   branch_kernel      per pattern f, f', f'' summed over site classes (with the per-class scale bookkeeping of
 //                      lfuntdd_SiteClass), then -sum fpatt log f etc.; deterministic block partials + cond_sum_kernel.
 // These are streaming kernels on the FP64 vector pipe (2 n^2 flops per pattern and son against 16 n bytes): at n = 61
-// compute-bound, at n = 4 HBM-bound.  First correct version: plain shared-memory tiles, no DMMA yet.
+// compute-bound, at n = 4 HBM-bound.  A thread owns one pattern and 8 consecutive states; the matrices sit TRANSPOSED in
+// shared memory so that those 8 entries of a column are four 128-bit broadcast loads per 8 FMAs (the first version read
+// two shared operands per multiply-add and was bound by the shared-memory pipe: ncu, profiles/).  No DMMA yet.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace pb200 {
 
 constexpr int COND_TP = 32;          // patterns per block (one per lane)
-constexpr int COND_THREADS = 256;    // 8 warps: warp w owns the states / rows  w, w+8, w+16, ...
+constexpr int COND_THREADS = 256;    // 8 warps: warp w owns the states / rows 8w .. 8w+7
+constexpr int COND_LDP = 64;         // leading dimension of the transposed matrices in shared memory (n <= 64, zero padded)
 
 struct CondNodeParams {
     int n, nclass, nnode, ns, ncodes, nson, node, scale_k, nscale;
     long long npatt, zstride;
     const int* sons;                 // [nson] node ids (device)
-    const double* P;                 // [nclass][nnode][n*n] plain row-major P(t) of every branch (by child node)
+    const double* P;                 // [nclass][nnode][n*n] P(t) of every branch (by child node), COLUMN-major: [k*n + j] = P[j][k]
     const unsigned char* z;          // [ns][zstride] compact codes
     const unsigned char* amb_n;      // [ncodes - n]
     const unsigned char* amb_map;    // [ncodes - n][64]
@@ -39,8 +42,8 @@ __global__ void __launch_bounds__(COND_THREADS) cond_node_kernel(const CondNodeP
 {
     extern __shared__ __align__(16) double csm[];
     const int n = p.n, LDT = n | 1;
-    double* Ps = csm;                          // [n][n]
-    double* tin = Ps + n * n;                  // [TP][LDT] a son's vectors
+    double* Pt = csm;                          // [n][COND_LDP] the son's P(t) TRANSPOSED: Pt[k][j] = P[j][k], columns >= n zero
+    double* tin = Pt + n * COND_LDP;           // [TP][LDT] a son's vectors
     double* tout = tin + COND_TP * LDT;        // [TP][LDT] this node's vectors
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, cls = blockIdx.y;
     const long long h0 = (long long)blockIdx.x * COND_TP, h = h0 + lane;
@@ -48,6 +51,7 @@ __global__ void __launch_bounds__(COND_THREADS) cond_node_kernel(const CondNodeP
     const bool valid = lane < nh;
     const size_t nint = (size_t)(p.nnode - p.ns);
     double* cbase = p.cond + (size_t)cls * nint * p.npatt * n;
+    const int j0 = 8 * w;                      // warp w owns the parent states 8w .. 8w+7 (one pattern per lane)
 
     double acc[8];
 #pragma unroll
@@ -55,52 +59,54 @@ __global__ void __launch_bounds__(COND_THREADS) cond_node_kernel(const CondNodeP
 
     for (int s = 0; s < p.nson; s++) {
         const int son = p.sons[s];
-        const double* Pm = p.P + ((size_t)cls * p.nnode + son) * n * n;
+        const double* Pm = p.P + ((size_t)cls * p.nnode + son) * n * n;     // column-major: Pm[k*n + j] = P[j][k]
         __syncthreads();                                        // previous son's tiles fully consumed
-        for (int e = tid; e < n * n; e += COND_THREADS) Ps[e] = Pm[e];
+        for (int e = tid; e < n * COND_LDP; e += COND_THREADS) { const int k = e / COND_LDP, j = e - k * COND_LDP; Pt[e] = (j < n) ? Pm[k * n + j] : 0.0; }
         if (son >= p.ns) {
             const double* src = cbase + ((size_t)(son - p.ns) * p.npatt + h0) * n;
             for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tin[hh * LDT + k] = src[e]; }
         }
         __syncthreads();
         if (valid) {
+            double t[8];
             if (son < p.ns) {                                   // tip: src/codeml.c:3555-3567
                 const int code = p.z[(size_t)son * p.zstride + h];
+                if (code < n) {
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    const int j = w + 8 * jj;
-                    if (j < n) {
-                        double t;
-                        if (code < n) t = Ps[j * n + code];
-                        else {
-                            const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
-                            const int cnt = p.amb_n[code - n];
-                            t = 0.0;
-                            for (int k = 0; k < cnt; k++) t = __dadd_rn(t, Ps[j * n + mp[k]]);
-                        }
-                        acc[jj] = __dmul_rn(acc[jj], t);
+                    for (int jj = 0; jj < 8; jj++) t[jj] = Pt[code * COND_LDP + j0 + jj];
+                }
+                else {
+                    const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
+                    const int cnt = p.amb_n[code - n];
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) t[jj] = 0.0;
+                    for (int k = 0; k < cnt; k++) {
+                        const double* q = Pt + mp[k] * COND_LDP + j0;
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) t[jj] += q[jj];
                     }
                 }
             }
             else {                                              // internal son: src/codeml.c:3568-3575
                 const double* v = tin + lane * LDT;
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    const int j = w + 8 * jj;
-                    if (j < n) {
-                        const double* pr = Ps + j * n;
-                        double t = 0.0;
-                        for (int k = 0; k < n; k++) t = __dadd_rn(t, __dmul_rn(pr[k], v[k]));
-                        acc[jj] = __dmul_rn(acc[jj], t);
-                    }
+                for (int jj = 0; jj < 8; jj++) t[jj] = 0.0;
+                for (int k = 0; k < n; k++) {                   // one per-lane load + four 128-bit broadcast loads per 8 FMAs
+                    const double vk = v[k];
+                    const double2* q = reinterpret_cast<const double2*>(Pt + k * COND_LDP + j0);
+                    const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+                    t[0] = fma(a.x, vk, t[0]); t[1] = fma(a.y, vk, t[1]); t[2] = fma(b.x, vk, t[2]); t[3] = fma(b.y, vk, t[3]);
+                    t[4] = fma(c.x, vk, t[4]); t[5] = fma(c.y, vk, t[5]); t[6] = fma(d.x, vk, t[6]); t[7] = fma(d.y, vk, t[7]);
                 }
             }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) acc[jj] *= t[jj];
         }
     }
     __syncthreads();
     if (valid) {
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) { const int j = w + 8 * jj; if (j < n) tout[lane * LDT + j] = acc[jj]; }
+        for (int jj = 0; jj < 8; jj++) if (j0 + jj < n) tout[lane * LDT + j0 + jj] = acc[jj];
     }
     __syncthreads();
     if (p.scale_k >= 0) {                                       // NodeScale, src/treesub.c:7214-7228
@@ -127,7 +133,7 @@ struct Pt3Params {
     const int* set_of_class;  // [nclass]
     const double* mult;       // [nclass] rgene * _rateSite * Qfactor (src/treesub.c:8435-8439)
     double t;
-    double* out;              // [nclass][3][n*n]
+    double* out;              // [nclass][3][n*n], each matrix COLUMN-major: [j*n + i] = P[i][j]
 };
 
 __global__ void __launch_bounds__(256) pt3_kernel(const Pt3Params p)
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(256) pt3_kernel(const Pt3Params p)
                 }
             }
         }
-        o[e] = P; o[n * n + e] = dP; o[2 * n * n + e] = ddP;
+        o[j * n + i] = P; o[n * n + j * n + i] = dP; o[2 * n * n + j * n + i] = ddP;
     }
 }
 
@@ -197,8 +203,8 @@ __global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams
 {
     extern __shared__ __align__(16) double bsm[];
     const int n = p.n, LDT = n | 1, nm = p.want_dd ? 3 : 1;
-    double* P3 = bsm;                           // [3][n][n]
-    double* tA = P3 + 3 * n * n;                // [TP][LDT]
+    double* P3 = bsm;                           // [3][n][COND_LDP] TRANSPOSED: P3[m][j][i] = (d^m P)[i][j], rows i >= n zero
+    double* tA = P3 + 3 * n * COND_LDP;         // [TP][LDT]
     double* tB = tA + COND_TP * LDT;            // [TP][LDT]
     double* red = tB + COND_TP * LDT;           // [3][8][TP]
     double* Sh = red + 3 * 8 * COND_TP;         // [TP]
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams
     const bool valid = lane < nh;
     const size_t nint = (size_t)(p.nnode - p.ns);
     const bool btip = p.b < p.ns;
+    const int i0 = 8 * w;                       // warp w owns the rows (states of b) 8w .. 8w+7
 
     // scale bookkeeping of lfuntdd_SiteClass (src/treesub.c:8437-8449): Sh = largest per-class sum of scale factors
     if (tid < COND_TP) {
@@ -225,7 +232,10 @@ __global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams
     for (int cls = 0; cls < p.nclass; cls++) {
         __syncthreads();
         const double* Pm = p.P3 + (size_t)cls * 3 * n * n;
-        for (int e = tid; e < nm * n * n; e += COND_THREADS) P3[e] = Pm[e];
+        for (int e = tid; e < nm * n * COND_LDP; e += COND_THREADS) {
+            const int m = e / (n * COND_LDP), r = e - m * n * COND_LDP, j = r / COND_LDP, i = r - j * COND_LDP;
+            P3[e] = (i < n) ? Pm[(size_t)m * n * n + j * n + i] : 0.0;
+        }
         const double* cb = p.cond + (size_t)cls * nint * p.npatt * n;
         {
             const double* src = cb + ((size_t)(p.a - p.ns) * p.npatt + h0) * n;
@@ -248,32 +258,54 @@ __global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams
                 }
             }
             const double* va = tA + lane * LDT;
-            int n1 = n, code = 0;
-            const unsigned char* mp = nullptr;
-            if (btip) {
-                code = p.z[(size_t)p.b * p.zstride + h];
-                if (code < n) n1 = 1;
-                else { n1 = p.amb_n[code - n]; mp = p.amb_map + (size_t)(code - n) * 64; }
-            }
-            for (int ii = w; ii < n1; ii += 8) {                // rows of P shared out over the 8 warps
-                int xb = ii;
-                double piqi;
-                if (btip) { xb = (code < n) ? code : mp[ii]; piqi = pK * p.pi[xb]; }
-                else piqi = pK * p.pi[ii] * tB[lane * LDT + ii];
-                const double* pr = P3 + xb * n;
-                double pq = 0.0, dpq = 0.0, ddpq = 0.0;
-                if (p.want_dd) {
-                    const double *dr = pr + n * n, *ddr = dr + n * n;
+            if (btip) {                                         // b is a tip: the states its code allows (src/treesub.c:8251-8256)
+                const int code = p.z[(size_t)p.b * p.zstride + h];
+                int n1 = 1;
+                const unsigned char* mp = nullptr;
+                if (code >= n) { n1 = p.amb_n[code - n]; mp = p.amb_map + (size_t)(code - n) * 64; }
+                for (int ii = w; ii < n1; ii += 8) {
+                    const int xb = (code < n) ? code : mp[ii];
+                    const double piqi = pK * p.pi[xb];
+                    double pq = 0.0, dpq = 0.0, ddpq = 0.0;
                     for (int j = 0; j < n; j++) {
                         const double aj = va[j];
-                        pq = __dadd_rn(pq, __dmul_rn(pr[j], aj));
-                        dpq = __dadd_rn(dpq, __dmul_rn(dr[j], aj));
-                        ddpq = __dadd_rn(ddpq, __dmul_rn(ddr[j], aj));
+                        pq = fma(P3[j * COND_LDP + xb], aj, pq);
+                        if (p.want_dd) {
+                            dpq = fma(P3[(n + j) * COND_LDP + xb], aj, dpq);
+                            ddpq = fma(P3[(2 * n + j) * COND_LDP + xb], aj, ddpq);
+                        }
+                    }
+                    f += piqi * pq; df += piqi * dpq; ddf += piqi * ddpq;
+                }
+            }
+            else {                                              // b internal: all n rows, 8 per warp
+                double pq[8], dpq[8], ddpq[8];
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) { pq[ii] = 0.0; dpq[ii] = 0.0; ddpq[ii] = 0.0; }
+                for (int j = 0; j < n; j++) {                   // one per-lane load + 128-bit broadcast loads per 8 (24) FMAs
+                    const double aj = va[j];
+                    const double2* q = reinterpret_cast<const double2*>(P3 + j * COND_LDP + i0);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const double2 x = q[u]; pq[2 * u] = fma(x.x, aj, pq[2 * u]); pq[2 * u + 1] = fma(x.y, aj, pq[2 * u + 1]); }
+                    if (p.want_dd) {
+                        const double2* q1 = reinterpret_cast<const double2*>(P3 + (n + j) * COND_LDP + i0);
+                        const double2* q2 = reinterpret_cast<const double2*>(P3 + (2 * n + j) * COND_LDP + i0);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const double2 x = q1[u], y = q2[u];
+                            dpq[2 * u] = fma(x.x, aj, dpq[2 * u]); dpq[2 * u + 1] = fma(x.y, aj, dpq[2 * u + 1]);
+                            ddpq[2 * u] = fma(y.x, aj, ddpq[2 * u]); ddpq[2 * u + 1] = fma(y.y, aj, ddpq[2 * u + 1]);
+                        }
                     }
                 }
-                else
-                    for (int j = 0; j < n; j++) pq = __dadd_rn(pq, __dmul_rn(pr[j], va[j]));
-                f += piqi * pq; df += piqi * dpq; ddf += piqi * ddpq;
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) {
+                    const int i = i0 + ii;
+                    if (i < n) {
+                        const double piqi = pK * p.pi[i] * tB[lane * LDT + i];
+                        f += piqi * pq[ii]; df += piqi * dpq[ii]; ddf += piqi * ddpq[ii];
+                    }
+                }
             }
         }
         red[(0 * 8 + w) * COND_TP + lane] = f;

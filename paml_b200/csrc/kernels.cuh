@@ -22,7 +22,7 @@ namespace pb200 {
 
 enum { KIND_UVROOT = 0, KIND_CIJK = 1, KIND_K80 = 2, KIND_JC69LIKE = 3, KIND_QMATEXP = 4 };
 enum { SEM_LFUN = 0, SEM_LFUNDG = 1 };
-enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2, PT_MODE_NUC4 = 3 };
+enum { PT_MODE_AUTO = -1, PT_MODE_TIP = 0, PT_MODE_FRAG = 1, PT_MODE_PLAIN = 2, PT_MODE_NUC4 = 3, PT_MODE_PLAIN_T = 4 };
 
 // Physical <-> logical state order inside a conditional vector.  The DMMA C fragment gives lane (g,q) the
 // physical columns 8nt+2q+e (e = 0,1); the A fragment of k-step ks wants column 4ks+q in that lane.  Storing
@@ -205,7 +205,10 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
             return;
         }
     }
-    if (mode == PT_MODE_PLAIN) {
+    if (mode == PT_MODE_PLAIN_T) {                           // column-major (cond.cuh): out[k*n + j] = P[j][k]
+        for (int e = tid; e < 16 * n; e += 256) { int r = e / n, k = e - r * n; if (i0 + r < n) out[(size_t)k * n + (i0 + r)] = Prow[r * ld + k]; }
+    }
+    else if (mode == PT_MODE_PLAIN) {
         for (int e = tid; e < 16 * n; e += 256) { int r = e / n, j = e - r * n; if (i0 + r < n) out[(size_t)(i0 + r) * n + j] = Prow[r * ld + j]; }
     }
     else if (mode == PT_MODE_TIP) {
