@@ -1184,23 +1184,26 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
         if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
                       (const double*)(ds + off_t), (double*)c->d_cP.p, (long long)n * n, PT_MODE_PLAIN_T, nnode, ns, c->NT, c->KS, c->ncodes))
             return 1;
-        const size_t smem = ((size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1)) * sizeof(double);
+        // tiles per block: enough blocks for two per SM, then as many tiles as that allows (a son's matrix is staged once per block)
+        const long long ntile = (c->npatt + COND_TP - 1) / COND_TP;
+        int tiles = (int)std::min<long long>(4, std::max<long long>(1, ntile * nclass / (2LL * c->nsm)));
+        const size_t smem = ((size_t)n * COND_LDP + (size_t)(1 + tiles) * COND_TP * (n | 1)) * sizeof(double);
         static bool attr_set[64] = {false};
         if (c->device < 64 && !attr_set[c->device]) {
-            CUDA_TRY(cudaFuncSetAttribute(cond_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 2 * COND_TP * 65) * 8));
+            CUDA_TRY(cudaFuncSetAttribute(cond_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 5 * COND_TP * 65) * 8));
             CUDA_TRY(cudaFuncSetAttribute(branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (3 * 64 * 64 + 2 * COND_TP * 65 + 3 * 8 * COND_TP + COND_TP) * 8));
+                                          (3 * 64 * 64 + 2 * COND_TP * 65 + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * 8));
             attr_set[c->device] = true;
         }
         for (int u = 0; u < nupd; u++) {
             CondNodeParams p;
             p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.nson = upd_nson[u]; p.node = upd_node[u];
-            p.scale_k = scale_k[upd_node[u]]; p.nscale = nscale; p.npatt = c->npatt; p.zstride = c->zstride;
+            p.scale_k = scale_k[upd_node[u]]; p.nscale = nscale; p.npatt = c->npatt; p.zstride = c->zstride; p.tiles = tiles;
             p.sons = (const int*)(ds + off_sons) + (size_t)u * maxsons;
             p.P = (const double*)c->d_cP.p; p.z = (const unsigned char*)c->d_z.p;
             p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
             p.cond = (double*)c->d_cond.p; p.scaleF = (double*)c->d_cscale.p;
-            dim3 grid((unsigned)((c->npatt + COND_TP - 1) / COND_TP), nclass);
+            dim3 grid((unsigned)((ntile + tiles - 1) / tiles), nclass);
             cond_node_kernel<<<grid, COND_THREADS, smem, c->stream>>>(p);
             c->launches++;
             CUDA_TRY(cudaGetLastError());
@@ -1228,7 +1231,9 @@ extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, i
     size_t off_s = align16(off_pi + (size_t)n * 8), off_r = align16(off_s + (size_t)nclass * 4), total = off_r + 32;
     if (!c->h_cbr) CUDA_TRY(cudaMallocHost(&c->h_cbr, 1 << 16));
     if (total > (1 << 16)) return fail("pb200_branch_lnl: too many classes");
-    const int nblk = (int)((c->npatt + COND_TP - 1) / COND_TP);
+    const long long ntile = (c->npatt + COND_TP - 1) / COND_TP;
+    const int tiles = (int)std::min<long long>(COND_TMAX, std::max<long long>(1, ntile / (2LL * c->nsm)));
+    const int nblk = (int)((ntile + tiles - 1) / tiles);
     if (c->d_cbr.ensure(total) || c->d_cP3.ensure((size_t)nclass * 3 * n * n * 8) || c->d_cpart.ensure((size_t)nblk * 3 * 8) || c->d_cres.ensure(32))
         return 1;
     char* hs = (char*)c->h_cbr;
@@ -1247,12 +1252,12 @@ extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, i
     CUDA_TRY(cudaGetLastError());
     BranchParams p;
     p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.a = a; p.b = b; p.nscale = c->cond_nscale;
-    p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride;
+    p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride; p.tiles = tiles;
     p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
     p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
     p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
     p.partial = (double*)c->d_cpart.p;
-    const size_t smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + COND_TP) * sizeof(double);
+    const size_t smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * sizeof(double);
     branch_kernel<<<nblk, COND_THREADS, smem, c->stream>>>(p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -24,10 +24,12 @@ namespace pb200 {
 
 constexpr int COND_TP = 32;          // patterns per block (one per lane)
 constexpr int COND_THREADS = 256;    // 8 warps: warp w owns the states / rows 8w .. 8w+7
+constexpr int COND_TMAX = 8;         // most tiles per block (COND_TMAX * COND_TP = COND_THREADS patterns)
 constexpr int COND_LDP = 64;         // leading dimension of the transposed matrices in shared memory (n <= 64, zero padded)
 
 struct CondNodeParams {
     int n, nclass, nnode, ns, ncodes, nson, node, scale_k, nscale;
+    int tiles;                       // tiles of COND_TP patterns per block: a son's matrix is staged once for all of them
     long long npatt, zstride;
     const int* sons;                 // [nson] node ids (device)
     const double* P;                 // [nclass][nnode][n*n] P(t) of every branch (by child node), COLUMN-major: [k*n + j] = P[j][k]
@@ -41,88 +43,92 @@ struct CondNodeParams {
 __global__ void __launch_bounds__(COND_THREADS) cond_node_kernel(const CondNodeParams p)
 {
     extern __shared__ __align__(16) double csm[];
-    const int n = p.n, LDT = n | 1;
+    const int n = p.n, LDT = n | 1, T = p.tiles;
     double* Pt = csm;                          // [n][COND_LDP] the son's P(t) TRANSPOSED: Pt[k][j] = P[j][k], columns >= n zero
-    double* tin = Pt + n * COND_LDP;           // [TP][LDT] a son's vectors
-    double* tout = tin + COND_TP * LDT;        // [TP][LDT] this node's vectors
+    double* tin = Pt + n * COND_LDP;           // [TP][LDT] a son's vectors, one tile
+    double* prod = tin + COND_TP * LDT;        // [T][TP][LDT] this node's vectors (running products over the sons)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, cls = blockIdx.y;
-    const long long h0 = (long long)blockIdx.x * COND_TP, h = h0 + lane;
-    const int nh = (int)min((long long)COND_TP, p.npatt - h0);
-    const bool valid = lane < nh;
+    const long long hb = (long long)blockIdx.x * T * COND_TP;        // the block's first pattern: it owns T tiles of TP patterns
     const size_t nint = (size_t)(p.nnode - p.ns);
     double* cbase = p.cond + (size_t)cls * nint * p.npatt * n;
     const int j0 = 8 * w;                      // warp w owns the parent states 8w .. 8w+7 (one pattern per lane)
 
-    double acc[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) acc[jj] = 1.0;             // src/codeml.c:3539-3540
-
     for (int s = 0; s < p.nson; s++) {
         const int son = p.sons[s];
         const double* Pm = p.P + ((size_t)cls * p.nnode + son) * n * n;     // column-major: Pm[k*n + j] = P[j][k]
-        __syncthreads();                                        // previous son's tiles fully consumed
+        __syncthreads();                                        // the previous son's matrix fully consumed
         for (int e = tid; e < n * COND_LDP; e += COND_THREADS) { const int k = e / COND_LDP, j = e - k * COND_LDP; Pt[e] = (j < n) ? Pm[k * n + j] : 0.0; }
-        if (son >= p.ns) {
-            const double* src = cbase + ((size_t)(son - p.ns) * p.npatt + h0) * n;
-            for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tin[hh * LDT + k] = src[e]; }
-        }
-        __syncthreads();
-        if (valid) {
-            double t[8];
-            if (son < p.ns) {                                   // tip: src/codeml.c:3555-3567
-                const int code = p.z[(size_t)son * p.zstride + h];
-                if (code < n) {
+        if (son < p.ns) __syncthreads();                        // (an internal son synchronises in the tile loop)
+        for (int tt = 0; tt < T; tt++) {                        // the matrix stays in shared memory for T tiles of patterns
+            const long long h0 = hb + (long long)tt * COND_TP;
+            if (h0 >= p.npatt) break;
+            const int nh = (int)min((long long)COND_TP, p.npatt - h0);
+            if (son >= p.ns) {
+                __syncthreads();                                // the previous tile's vectors fully consumed
+                const double* src = cbase + ((size_t)(son - p.ns) * p.npatt + h0) * n;
+                for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tin[hh * LDT + k] = src[e]; }
+                __syncthreads();
+            }
+            if (lane < nh) {
+                double t[8];
+                if (son < p.ns) {                               // tip: src/codeml.c:3555-3567
+                    const int code = p.z[(size_t)son * p.zstride + h0 + lane];
+                    if (code < n) {
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++) t[jj] = Pt[code * COND_LDP + j0 + jj];
-                }
-                else {
-                    const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
-                    const int cnt = p.amb_n[code - n];
+                        for (int jj = 0; jj < 8; jj++) t[jj] = Pt[code * COND_LDP + j0 + jj];
+                    }
+                    else {
+                        const unsigned char* mp = p.amb_map + (size_t)(code - n) * 64;
+                        const int cnt = p.amb_n[code - n];
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++) t[jj] = 0.0;
-                    for (int k = 0; k < cnt; k++) {
-                        const double* q = Pt + mp[k] * COND_LDP + j0;
+                        for (int jj = 0; jj < 8; jj++) t[jj] = 0.0;
+                        for (int k = 0; k < cnt; k++) {
+                            const double* q = Pt + mp[k] * COND_LDP + j0;
 #pragma unroll
-                        for (int jj = 0; jj < 8; jj++) t[jj] += q[jj];
+                            for (int jj = 0; jj < 8; jj++) t[jj] += q[jj];
+                        }
                     }
                 }
-            }
-            else {                                              // internal son: src/codeml.c:3568-3575
-                const double* v = tin + lane * LDT;
+                else {                                          // internal son: src/codeml.c:3568-3575
+                    const double* v = tin + lane * LDT;
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) t[jj] = 0.0;
-                for (int k = 0; k < n; k++) {                   // one per-lane load + four 128-bit broadcast loads per 8 FMAs
-                    const double vk = v[k];
-                    const double2* q = reinterpret_cast<const double2*>(Pt + k * COND_LDP + j0);
-                    const double2 a = q[0], b = q[1], c = q[2], d = q[3];
-                    t[0] = fma(a.x, vk, t[0]); t[1] = fma(a.y, vk, t[1]); t[2] = fma(b.x, vk, t[2]); t[3] = fma(b.y, vk, t[3]);
-                    t[4] = fma(c.x, vk, t[4]); t[5] = fma(c.y, vk, t[5]); t[6] = fma(d.x, vk, t[6]); t[7] = fma(d.y, vk, t[7]);
+                    for (int jj = 0; jj < 8; jj++) t[jj] = 0.0;
+                    for (int k = 0; k < n; k++) {               // one per-lane load + four 128-bit broadcast loads per 8 FMAs
+                        const double vk = v[k];
+                        const double2* q = reinterpret_cast<const double2*>(Pt + k * COND_LDP + j0);
+                        const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+                        t[0] = fma(a.x, vk, t[0]); t[1] = fma(a.y, vk, t[1]); t[2] = fma(b.x, vk, t[2]); t[3] = fma(b.y, vk, t[3]);
+                        t[4] = fma(c.x, vk, t[4]); t[5] = fma(c.y, vk, t[5]); t[6] = fma(d.x, vk, t[6]); t[7] = fma(d.y, vk, t[7]);
+                    }
                 }
+                double* o = prod + ((size_t)tt * COND_TP + lane) * LDT + j0;      // this thread's own 8 entries: no race
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++)
+                    if (j0 + jj < n) o[jj] = (s == 0) ? t[jj] : o[jj] * t[jj];   // 1 * first son (src/codeml.c:3539-3540)
             }
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++) acc[jj] *= t[jj];
         }
     }
     __syncthreads();
-    if (valid) {
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) if (j0 + jj < n) tout[lane * LDT + j0 + jj] = acc[jj];
-    }
-    __syncthreads();
-    if (p.scale_k >= 0) {                                       // NodeScale, src/treesub.c:7214-7228
-        if (tid < nh) {
-            double* v = tout + tid * LDT;
-            double t = 0.0;
-            for (int j = 0; j < n; j++) if (v[j] > t) t = v[j];
-            double f;
-            if (t < 1e-300) { for (int j = 0; j < n; j++) v[j] = 1.0; f = -800.0; }
-            else { for (int j = 0; j < n; j++) v[j] = v[j] / t; f = log(t); }
-            p.scaleF[((size_t)cls * p.nscale + p.scale_k) * p.npatt + h0 + tid] = f;
+    for (int tt = 0; tt < T; tt++) {
+        const long long h0 = hb + (long long)tt * COND_TP;
+        if (h0 >= p.npatt) break;
+        const int nh = (int)min((long long)COND_TP, p.npatt - h0);
+        double* tout = prod + (size_t)tt * COND_TP * LDT;
+        if (p.scale_k >= 0) {                                   // NodeScale, src/treesub.c:7214-7228
+            if (tid < nh) {
+                double* v = tout + tid * LDT;
+                double t = 0.0;
+                for (int j = 0; j < n; j++) if (v[j] > t) t = v[j];
+                double f;
+                if (t < 1e-300) { for (int j = 0; j < n; j++) v[j] = 1.0; f = -800.0; }
+                else { for (int j = 0; j < n; j++) v[j] = v[j] / t; f = log(t); }
+                p.scaleF[((size_t)cls * p.nscale + p.scale_k) * p.npatt + h0 + tid] = f;
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        double* dst = cbase + ((size_t)(p.node - p.ns) * p.npatt + h0) * n;
+        for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; dst[e] = tout[hh * LDT + k]; }
     }
-    double* dst = cbase + ((size_t)(p.node - p.ns) * p.npatt + h0) * n;
-    for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; dst[e] = tout[hh * LDT + k]; }
 }
 
 // ---- P, P', P'' of the branch being optimised ----
@@ -186,6 +192,7 @@ enum { BR_SEM_LFUNT = 0, BR_SEM_SITECLASS = 1 };
 
 struct BranchParams {
     int n, nclass, nnode, ns, ncodes, a, b, nscale, semantics, want_dd;
+    int tiles;                 // tiles of COND_TP patterns per block (<= COND_TMAX): P, P', P'' are staged once per class for all of them
     long long npatt, zstride;
     const double* P3;          // [nclass][3][n*n]
     const double* cond;        // [nclass][nint][npatt][n]
@@ -202,148 +209,163 @@ struct BranchParams {
 __global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams p)
 {
     extern __shared__ __align__(16) double bsm[];
-    const int n = p.n, LDT = n | 1, nm = p.want_dd ? 3 : 1;
+    const int n = p.n, LDT = n | 1, nm = p.want_dd ? 3 : 1, T = p.tiles;
     double* P3 = bsm;                           // [3][n][COND_LDP] TRANSPOSED: P3[m][j][i] = (d^m P)[i][j], rows i >= n zero
     double* tA = P3 + 3 * n * COND_LDP;         // [TP][LDT]
     double* tB = tA + COND_TP * LDT;            // [TP][LDT]
-    double* red = tB + COND_TP * LDT;           // [3][8][TP]
-    double* Sh = red + 3 * 8 * COND_TP;         // [TP]
+    double* red = tB + COND_TP * LDT;           // [3][8][TP]   (reused as [3][256] for the final block sum)
+    double* Sh = red + 3 * 8 * COND_TP;         // [COND_TMAX][TP]
+    double* facc = Sh + COND_TMAX * COND_TP;    // [3][COND_TMAX][TP] f, f', f'' of the block's patterns, summed over the classes
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const long long h0 = (long long)blockIdx.x * COND_TP, h = h0 + lane;
-    const int nh = (int)min((long long)COND_TP, p.npatt - h0);
-    const bool valid = lane < nh;
+    const long long hb = (long long)blockIdx.x * T * COND_TP;      // the block owns T tiles of TP patterns
     const size_t nint = (size_t)(p.nnode - p.ns);
     const bool btip = p.b < p.ns;
     const int i0 = 8 * w;                       // warp w owns the rows (states of b) 8w .. 8w+7
 
     // scale bookkeeping of lfuntdd_SiteClass (src/treesub.c:8437-8449): Sh = largest per-class sum of scale factors
-    if (tid < COND_TP) {
+    if (tid < T * COND_TP) {
         double best = 0.0;
-        if (p.nscale > 0 && tid < nh) {
+        const long long h = hb + tid;
+        if (p.nscale > 0 && h < p.npatt) {
             for (int ir = 0; ir < p.nclass; ir++) {
                 double y = 0.0;
-                for (int k = 0; k < p.nscale; k++) y += p.scaleF[((size_t)ir * p.nscale + k) * p.npatt + h0 + tid];
+                for (int k = 0; k < p.nscale; k++) y += p.scaleF[((size_t)ir * p.nscale + k) * p.npatt + h];
                 if (ir == 0 || y > best) best = y;
             }
         }
         Sh[tid] = best;
+        facc[tid] = 0.0; facc[COND_TMAX * COND_TP + tid] = 0.0; facc[2 * COND_TMAX * COND_TP + tid] = 0.0;
     }
-    double fh = 0.0, dfh = 0.0, ddfh = 0.0;      // lanes of warp 0 accumulate over the classes
     for (int cls = 0; cls < p.nclass; cls++) {
-        __syncthreads();
+        __syncthreads();                                        // the previous class's matrices fully consumed
         const double* Pm = p.P3 + (size_t)cls * 3 * n * n;
         for (int e = tid; e < nm * n * COND_LDP; e += COND_THREADS) {
             const int m = e / (n * COND_LDP), r = e - m * n * COND_LDP, j = r / COND_LDP, i = r - j * COND_LDP;
             P3[e] = (i < n) ? Pm[(size_t)m * n * n + j * n + i] : 0.0;
         }
         const double* cb = p.cond + (size_t)cls * nint * p.npatt * n;
-        {
-            const double* src = cb + ((size_t)(p.a - p.ns) * p.npatt + h0) * n;
-            for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tA[hh * LDT + k] = src[e]; }
-        }
-        if (!btip) {
-            const double* src = cb + ((size_t)(p.b - p.ns) * p.npatt + h0) * n;
-            for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tB[hh * LDT + k] = src[e]; }
-        }
-        __syncthreads();
-        double f = 0.0, df = 0.0, ddf = 0.0;
-        if (valid) {
-            double pK = 1.0;
-            if (p.semantics == BR_SEM_SITECLASS) {
-                pK = p.freqK[cls];
-                if (p.nscale > 0) {
-                    double y = 0.0;
-                    for (int k = 0; k < p.nscale; k++) y += p.scaleF[((size_t)cls * p.nscale + k) * p.npatt + h];
-                    pK = pK * exp(y - Sh[lane]);
-                }
+        for (int tt = 0; tt < T; tt++) {                        // the three matrices stay in shared memory for T tiles
+            const long long h0 = hb + (long long)tt * COND_TP, h = h0 + lane;
+            if (h0 >= p.npatt) break;
+            const int nh = (int)min((long long)COND_TP, p.npatt - h0);
+            __syncthreads();                                    // previous tile's vectors and partial sums fully consumed
+            {
+                const double* src = cb + ((size_t)(p.a - p.ns) * p.npatt + h0) * n;
+                for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tA[hh * LDT + k] = src[e]; }
             }
-            const double* va = tA + lane * LDT;
-            if (btip) {                                         // b is a tip: the states its code allows (src/treesub.c:8251-8256)
-                const int code = p.z[(size_t)p.b * p.zstride + h];
-                int n1 = 1;
-                const unsigned char* mp = nullptr;
-                if (code >= n) { n1 = p.amb_n[code - n]; mp = p.amb_map + (size_t)(code - n) * 64; }
-                for (int ii = w; ii < n1; ii += 8) {
-                    const int xb = (code < n) ? code : mp[ii];
-                    const double piqi = pK * p.pi[xb];
-                    double pq = 0.0, dpq = 0.0, ddpq = 0.0;
-                    for (int j = 0; j < n; j++) {
+            if (!btip) {
+                const double* src = cb + ((size_t)(p.b - p.ns) * p.npatt + h0) * n;
+                for (int e = tid; e < nh * n; e += COND_THREADS) { const int hh = e / n, k = e - hh * n; tB[hh * LDT + k] = src[e]; }
+            }
+            __syncthreads();
+            double f = 0.0, df = 0.0, ddf = 0.0;
+            if (lane < nh) {
+                double pK = 1.0;
+                if (p.semantics == BR_SEM_SITECLASS) {
+                    pK = p.freqK[cls];
+                    if (p.nscale > 0) {
+                        double y = 0.0;
+                        for (int k = 0; k < p.nscale; k++) y += p.scaleF[((size_t)cls * p.nscale + k) * p.npatt + h];
+                        pK = pK * exp(y - Sh[tt * COND_TP + lane]);
+                    }
+                }
+                const double* va = tA + lane * LDT;
+                if (btip) {                                     // b is a tip: the states its code allows (src/treesub.c:8251-8256)
+                    const int code = p.z[(size_t)p.b * p.zstride + h];
+                    int n1 = 1;
+                    const unsigned char* mp = nullptr;
+                    if (code >= n) { n1 = p.amb_n[code - n]; mp = p.amb_map + (size_t)(code - n) * 64; }
+                    for (int ii = w; ii < n1; ii += 8) {
+                        const int xb = (code < n) ? code : mp[ii];
+                        const double piqi = pK * p.pi[xb];
+                        double pq = 0.0, dpq = 0.0, ddpq = 0.0;
+                        for (int j = 0; j < n; j++) {
+                            const double aj = va[j];
+                            pq = fma(P3[j * COND_LDP + xb], aj, pq);
+                            if (p.want_dd) {
+                                dpq = fma(P3[(n + j) * COND_LDP + xb], aj, dpq);
+                                ddpq = fma(P3[(2 * n + j) * COND_LDP + xb], aj, ddpq);
+                            }
+                        }
+                        f += piqi * pq; df += piqi * dpq; ddf += piqi * ddpq;
+                    }
+                }
+                else {                                          // b internal: all n rows, 8 per warp
+                    double pq[8], dpq[8], ddpq[8];
+#pragma unroll
+                    for (int ii = 0; ii < 8; ii++) { pq[ii] = 0.0; dpq[ii] = 0.0; ddpq[ii] = 0.0; }
+                    for (int j = 0; j < n; j++) {               // one per-lane load + 128-bit broadcast loads per 8 (24) FMAs
                         const double aj = va[j];
-                        pq = fma(P3[j * COND_LDP + xb], aj, pq);
+                        const double2* q = reinterpret_cast<const double2*>(P3 + j * COND_LDP + i0);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { const double2 x = q[u]; pq[2 * u] = fma(x.x, aj, pq[2 * u]); pq[2 * u + 1] = fma(x.y, aj, pq[2 * u + 1]); }
                         if (p.want_dd) {
-                            dpq = fma(P3[(n + j) * COND_LDP + xb], aj, dpq);
-                            ddpq = fma(P3[(2 * n + j) * COND_LDP + xb], aj, ddpq);
+                            const double2* q1 = reinterpret_cast<const double2*>(P3 + (n + j) * COND_LDP + i0);
+                            const double2* q2 = reinterpret_cast<const double2*>(P3 + (2 * n + j) * COND_LDP + i0);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const double2 x = q1[u], y = q2[u];
+                                dpq[2 * u] = fma(x.x, aj, dpq[2 * u]); dpq[2 * u + 1] = fma(x.y, aj, dpq[2 * u + 1]);
+                                ddpq[2 * u] = fma(y.x, aj, ddpq[2 * u]); ddpq[2 * u + 1] = fma(y.y, aj, ddpq[2 * u + 1]);
+                            }
                         }
                     }
-                    f += piqi * pq; df += piqi * dpq; ddf += piqi * ddpq;
-                }
-            }
-            else {                                              // b internal: all n rows, 8 per warp
-                double pq[8], dpq[8], ddpq[8];
 #pragma unroll
-                for (int ii = 0; ii < 8; ii++) { pq[ii] = 0.0; dpq[ii] = 0.0; ddpq[ii] = 0.0; }
-                for (int j = 0; j < n; j++) {                   // one per-lane load + 128-bit broadcast loads per 8 (24) FMAs
-                    const double aj = va[j];
-                    const double2* q = reinterpret_cast<const double2*>(P3 + j * COND_LDP + i0);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) { const double2 x = q[u]; pq[2 * u] = fma(x.x, aj, pq[2 * u]); pq[2 * u + 1] = fma(x.y, aj, pq[2 * u + 1]); }
-                    if (p.want_dd) {
-                        const double2* q1 = reinterpret_cast<const double2*>(P3 + (n + j) * COND_LDP + i0);
-                        const double2* q2 = reinterpret_cast<const double2*>(P3 + (2 * n + j) * COND_LDP + i0);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const double2 x = q1[u], y = q2[u];
-                            dpq[2 * u] = fma(x.x, aj, dpq[2 * u]); dpq[2 * u + 1] = fma(x.y, aj, dpq[2 * u + 1]);
-                            ddpq[2 * u] = fma(y.x, aj, ddpq[2 * u]); ddpq[2 * u + 1] = fma(y.y, aj, ddpq[2 * u + 1]);
+                    for (int ii = 0; ii < 8; ii++) {
+                        const int i = i0 + ii;
+                        if (i < n) {
+                            const double piqi = pK * p.pi[i] * tB[lane * LDT + i];
+                            f += piqi * pq[ii]; df += piqi * dpq[ii]; ddf += piqi * ddpq[ii];
                         }
                     }
                 }
-#pragma unroll
-                for (int ii = 0; ii < 8; ii++) {
-                    const int i = i0 + ii;
-                    if (i < n) {
-                        const double piqi = pK * p.pi[i] * tB[lane * LDT + i];
-                        f += piqi * pq[ii]; df += piqi * dpq[ii]; ddf += piqi * ddpq[ii];
-                    }
-                }
             }
-        }
-        red[(0 * 8 + w) * COND_TP + lane] = f;
-        red[(1 * 8 + w) * COND_TP + lane] = df;
-        red[(2 * 8 + w) * COND_TP + lane] = ddf;
-        __syncthreads();
-        if (w == 0) {
-            for (int ww = 0; ww < 8; ww++) {
-                fh += red[(0 * 8 + ww) * COND_TP + lane];
-                dfh += red[(1 * 8 + ww) * COND_TP + lane];
-                ddfh += red[(2 * 8 + ww) * COND_TP + lane];
+            red[(0 * 8 + w) * COND_TP + lane] = f;
+            red[(1 * 8 + w) * COND_TP + lane] = df;
+            red[(2 * 8 + w) * COND_TP + lane] = ddf;
+            __syncthreads();
+            if (w == 0) {                                       // fixed order over the 8 warps, then over the classes
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                for (int ww = 0; ww < 8; ww++) {
+                    a0 += red[(0 * 8 + ww) * COND_TP + lane];
+                    a1 += red[(1 * 8 + ww) * COND_TP + lane];
+                    a2 += red[(2 * 8 + ww) * COND_TP + lane];
+                }
+                facc[tt * COND_TP + lane] += a0;
+                facc[(COND_TMAX + tt) * COND_TP + lane] += a1;
+                facc[(2 * COND_TMAX + tt) * COND_TP + lane] += a2;
             }
         }
     }
-    if (w == 0) {
-        double l = 0.0, dl = 0.0, ddl = 0.0;
-        if (valid) {
+    __syncthreads();
+    // per pattern -lnL and its derivatives (src/treesub.c:8531-8540), then a fixed-order block sum
+    double l = 0.0, dl = 0.0, ddl = 0.0;
+    if (tid < T * COND_TP) {
+        const long long h = hb + tid;
+        if (h < p.npatt) {
             const double fp = p.fpatt[h];
             if (fp != 0.0) {
+                const double fh = facc[tid], dfh = facc[COND_TMAX * COND_TP + tid], ddfh = facc[2 * COND_TMAX * COND_TP + tid];
                 const double lf = (p.semantics == BR_SEM_LFUNT && !p.want_dd && fh < 0) ? -500.0 : log(fh);   // src/treesub.c:8192-8193
                 l = -(lf * fp);
-                if (p.nscale > 0) l -= Sh[lane] * fp;
+                if (p.nscale > 0) l -= Sh[tid] * fp;
                 if (p.want_dd) {
                     dl = -(dfh / fh * fp);
                     ddl = -((fh * ddfh - dfh * dfh) / (fh * fh) * fp);
                 }
             }
         }
-        for (int o = 16; o > 0; o >>= 1) {                      // fixed-order tree: the sums are reproducible call to call
-            l += __shfl_down_sync(0xffffffffu, l, o);
-            dl += __shfl_down_sync(0xffffffffu, dl, o);
-            ddl += __shfl_down_sync(0xffffffffu, ddl, o);
-        }
-        if (lane == 0) {
-            p.partial[(size_t)blockIdx.x * 3 + 0] = l;
-            p.partial[(size_t)blockIdx.x * 3 + 1] = dl;
-            p.partial[(size_t)blockIdx.x * 3 + 2] = ddl;
-        }
+    }
+    red[tid] = l; red[256 + tid] = dl; red[512 + tid] = ddl;    // red has 3 * 8 * TP = 768 doubles
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { red[tid] += red[tid + o]; red[256 + tid] += red[256 + tid + o]; red[512 + tid] += red[512 + tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.partial[(size_t)blockIdx.x * 3 + 0] = red[0];
+        p.partial[(size_t)blockIdx.x * 3 + 1] = red[256];
+        p.partial[(size_t)blockIdx.x * 3 + 2] = red[512];
     }
 }
 
