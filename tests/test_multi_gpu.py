@@ -65,3 +65,52 @@ def test_dropin_two_gpus(tmp_path):
         assert r.returncode == 0, r.stdout[-2000:]
         vals.append(float(re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d / "mlc").read())[-1]))
     assert abs(vals[0] - vals[1]) <= 1e-9 * abs(vals[0]), vals
+
+
+def _fit_lnl(exe, d, env, outfile):
+    r = subprocess.run([exe, "run.ctl"], cwd=str(d), env=dict(os.environ, **env), stdin=subprocess.DEVNULL,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    return float(re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d / outfile).read())[-1])
+
+
+def test_dropin_two_gpus_method1(tmp_path):
+    """method = 1 with the patterns sharded over two GPUs: every shard keeps its own HBM-resident conditional vectors, the
+    shim adds the shards' -lnL, d/dt and d2/dt2 of every Newton step (paml_b200/host/plfun_b200.inc, pbh_mb_branch)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from paml_b200 import paml_io
+    exe = os.path.join(REPO, "paml_b200", "bin", "codeml_b200")
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt binary missing")
+    p = simulate.codon_m0_problem(ns=8, npatt=600, seed=71)
+    vals = []
+    for ng in (1, 2):
+        d = tmp_path / ("g%d" % ng); d.mkdir()
+        paml_io.write_pattern_files(p, str(d / "s"))
+        paml_io.write_codeml_ctl(str(d / "run.ctl"), "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
+        vals.append(_fit_lnl(exe, d, dict(PB200_NGPU=str(ng)), "mlc"))
+    assert abs(vals[0] - vals[1]) <= 2e-6 * abs(vals[0]), vals
+
+
+def test_dropin_two_gpus_genes(tmp_path):
+    """Two partitions with their own kappa and pi (Mgene = 4): gene g is evaluated on GPU g % 2."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from paml_b200 import paml_io
+    exe = os.path.join(REPO, "paml_b200", "bin", "baseml_b200")
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt binary missing")
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=200, seed=33, K=4)
+    n = int(p.npatt)
+    vals = []
+    for ng in (1, 2):
+        d = tmp_path / ("g%d" % ng); d.mkdir()
+        paml_io.write_pattern_files(p, str(d / "s"), genes=[n - n // 3, n // 3])
+        with open(d / "run.ctl", "w") as f:
+            f.write("seqfile = s.phy\ntreefile = s.tre\noutfile = mlb\nnoisy = 0\nverbose = 0\nrunmode = 0\nMgene = 4\nclock = 0\n"
+                    "Malpha = 1\ngetSE = 0\nRateAncestor = 0\nSmall_Diff = 7e-6\ncleandata = 1\nmethod = 0\nmodel = 4\nfix_kappa = 0\n"
+                    "kappa = 2\nfix_alpha = 0\nalpha = 0.5\nncatG = 4\nnhomo = 0\nfix_blength = 1\n")
+        vals.append(_fit_lnl(exe, d, dict(PB200_NGPU=str(ng)), "mlb"))
+    assert abs(vals[0] - vals[1]) <= 2e-6 * abs(vals[0]), vals
