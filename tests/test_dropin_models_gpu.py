@@ -267,19 +267,40 @@ def test_method1_codeml_40_taxa_with_scaling_nodes(tmp_path):
     _close_method1(_both(tmp_path, "codeml", write, "mlc"), "codeml", lambda d: write(d, 0), "mlc", tmp_path)
 
 
-def test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path):
-    """Where minbranches is NOT mapped to the GPU (here K80: closed-form P(t), no spectral set; and PB200_MINB=0) the
-    reference's CPU routines run on nodes[].conP, which the GPU likelihood never fills: the shim refreshes them with the
-    reference's own CPU evaluation first.  (Without that the fit converges to a wrong optimum.)"""
+@pytest.mark.parametrize("model,nhomo", [(1, 0), (0, 0), (4, 2), (1, 2)])
+def test_method1_baseml_k80_and_kappa_per_branch(tmp_path, model, nhomo):
+    """K80 / JC69 (closed-form P(t) in the evaluation path, their Cijk form under minbranches, as in lfunt) and nhomo = 2
+    (kappa per branch: one Cijk set per branch, lfunt's per-branch eigenTN93, src/treesub.c:8149-8152)."""
     p = simulate.nuc_gtr_gamma_problem(ns=8, npatt=300, seed=26, K=1)
 
-    def write(d):
+    def write(d, method=1):
         paml_io.write_pattern_files(p, d + "/s")
         with open(d + "/run.ctl", "w") as f:
-            f.write((BASEML_CTL % dict(Mgene=0, Malpha=0, model=1, fix_alpha=1, alpha="0", ncatG=1, nhomo=0, more=""))
-                    .replace("method = 0", "method = 1"))
-    _close(_both(tmp_path / "k80", "baseml", write, "mlb"), 2e-6)
+            f.write((BASEML_CTL % dict(Mgene=0, Malpha=0, model=model, fix_alpha=1, alpha="0", ncatG=1, nhomo=nhomo, more=""))
+                    .replace("method = 0", "method = %d" % method))
+    res = _both(tmp_path, "baseml", write, "mlb")
+    _close_method1(res, "baseml", lambda d: write(d, 0), "mlb", tmp_path)
+    _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "baseml_b200"))
 
+
+def test_method1_codeml_free_ratio(tmp_path):
+    """model = 1 under method = 1: lfunt / lfuntdd solve an eigen-problem for the branch at every call (src/treesub.c:8137-8146);
+    the drop-in keeps one spectral set per branch (memoised) resident for pb200_branch_lnl."""
+    p = simulate.codon_m0_problem(ns=8, npatt=200, seed=43)
+
+    def write(d, method=1):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", model=1, kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=method))
+    res = _both(tmp_path, "codeml", write, "mlc")
+    _close_method1(res, "codeml", lambda d: write(d, 0), "mlc", tmp_path, rel=5e-6)
+    _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "codeml_b200"))
+
+
+def test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path):
+    """Where minbranches is NOT mapped to the GPU (PB200_MINB=0 forces that here) the reference's CPU routines run on
+    nodes[].conP, which the GPU likelihood never fills: the shim refreshes them with the reference's own CPU evaluation
+    first.  (Without that the fit converges to a wrong optimum.)"""
     q = simulate.codon_m0_problem(ns=8, npatt=300, seed=71)
     ref = None
     for tag, exe, env in (("ref", os.path.join(REF, "codeml"), {}), ("cpu_minb", os.path.join(BIN, "codeml_b200"), {"PB200_MINB": "0"})):

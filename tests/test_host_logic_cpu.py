@@ -103,6 +103,15 @@ def test_method1_hky_gamma(shim, tmp_path):
     T.test_method1_baseml_hky_gamma(tmp_path)
 
 
+@pytest.mark.parametrize("model,nhomo", [(1, 0), (0, 0), (4, 2), (1, 2)])
+def test_method1_k80_and_kappa_per_branch(shim, tmp_path, model, nhomo):
+    T.test_method1_baseml_k80_and_kappa_per_branch(tmp_path, model, nhomo)
+
+
+def test_method1_free_ratio(shim, tmp_path):
+    T.test_method1_codeml_free_ratio(tmp_path)
+
+
 def test_method1_cpu_minbranches_paths(shim, tmp_path):
     T.test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path)
 
