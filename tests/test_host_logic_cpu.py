@@ -122,3 +122,83 @@ def test_method1_ancestral(shim, tmp_path):
 
 def test_too_many_genes_fails_loudly(shim, tmp_path):
     T.test_too_many_genes_fails_loudly(tmp_path)
+
+
+# ---- scenarios that exist only here (callers of com.plfun / fx_r whose GPU side is nothing but the evaluations above) ----
+
+def _run_pair(shim, tmp_path, prog, write):
+    out = {}
+    for tag, exe in (("gpu", os.path.join(shim, prog + "_b200")), ("ref", os.path.join(REPO, "oracle", "_ref", prog))):
+        d = tmp_path / tag
+        d.mkdir()
+        write(str(d))
+        T._run(exe, str(d))
+        out[tag] = str(d)
+    return out
+
+
+def test_standard_errors_hessian(shim, tmp_path):
+    """getSE = 1: the Hessian by second differences of com.plfun (HessianSKT2004 / Hessian, src/treesub.c:7241, src/tools.c);
+    the standard errors printed in the main result file must agree with the reference's."""
+    import re
+    from paml_b200 import paml_io, simulate
+    p = simulate.codon_m0_problem(ns=6, npatt=250, seed=81)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, getSE=1))
+    dirs = _run_pair(shim, tmp_path, "codeml", write)
+    se = {}
+    for tag, d in dirs.items():
+        txt = open(d + "/mlc").read()
+        m = re.search(r"SEs for parameters:\s*\n([^\n]+)\n", txt)
+        assert m, "no SE block in " + d
+        se[tag] = [float(v) for v in m.group(1).split()]
+    assert len(se["gpu"]) == len(se["ref"]) == 11
+    for a, b in zip(se["gpu"], se["ref"]):
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-2), (se["gpu"], se["ref"])
+
+
+def test_rates_for_sites_and_ancestors_method0(shim, tmp_path):
+    """RateAncestor = 1 with gamma rates under method = 0: lfunRates reads com.fhK as left by fx_r (the GPU path), the
+    marginal reconstruction runs the reference's CPU ConditionalPNode; `rates` and `rst` must agree with the reference's."""
+    from paml_b200 import paml_io, simulate
+    p = simulate.nuc_gtr_gamma_problem(ns=8, npatt=300, seed=25, K=4)
+
+    def write(d):
+        paml_io.write_sequence_files(p, d + "/s")
+        with open(d + "/run.ctl", "w") as f:
+            f.write((T.BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=0, alpha="0.5", ncatG=4, nhomo=0, more=""))
+                    .replace("RateAncestor = 0", "RateAncestor = 1"))
+    dirs = _run_pair(shim, tmp_path, "baseml", write)
+    assert abs(T._lnl(dirs["gpu"] + "/mlb") - T._lnl(dirs["ref"] + "/mlb")) <= 2e-6 * abs(T._lnl(dirs["ref"] + "/mlb"))
+    for fn, least in (("rates", 300), ("rst", 500)):
+        g, r = T._numbers(dirs["gpu"] + "/" + fn), T._numbers(dirs["ref"] + "/" + fn)
+        assert len(g) == len(r) and len(r) > least, (fn, len(g), len(r))
+        bad = [(a, b) for (a, da), (b, db) in zip(g, r) if abs(a - b) > 2e-3 + 2.5 * 10.0 ** (-min(da, db))]
+        assert not bad, (fn, bad[:10])
+
+
+@pytest.mark.parametrize("tag,extra,method", [("branch", dict(model=2), 0), ("branch", dict(model=2), 1),
+                                             ("branch_site_A", dict(model=2, NSsites=2, ncatG=3), 0),
+                                             ("branch_site_A", dict(model=2, NSsites=2, ncatG=3), 1)])
+def test_labelled_branches(shim, tmp_path, tag, extra, method):
+    """Branch model (model = 2: omega per branch label, the _UU[] sets) and branch-site model A (Set_UVR_BranchSite, Qfactor per
+    label), with the simultaneous optimiser and with method = 1 (where lfuntdd[_SiteClass] pick the set by the label of the
+    branch under iteration): a foreground clade marked #1 in the tree file."""
+    from paml_b200 import paml_io, simulate
+    p = simulate.codon_m0_problem(ns=8, npatt=(90 if "NSsites" in extra else 200), seed=45)
+
+    def write(d, m=method):
+        paml_io.write_pattern_files(p, d + "/s")
+        tre = open(d + "/s.tre").read()
+        i = tre.index("):")
+        open(d + "/s.tre", "w").write(tre[:i + 1] + " #1 " + tre[i + 1:])
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=m, **extra))
+    res = T._both(tmp_path, "codeml", write, "mlc")
+    if method == 1:
+        T._close_method1(res, "codeml", lambda d: write(d, 0), "mlc", tmp_path, rel=5e-6)
+    else:
+        T._close(res, 5e-6)
