@@ -202,3 +202,98 @@ def test_labelled_branches(shim, tmp_path, tag, extra, method):
         T._close_method1(res, "codeml", lambda d: write(d, 0), "mlc", tmp_path, rel=5e-6)
     else:
         T._close(res, 5e-6)
+
+
+@pytest.mark.parametrize("prog", ["baseml", "codeml"])
+def test_global_clock(shim, tmp_path, prog):
+    """clock = 1 on a rooted tree: node ages are the parameters, t of every branch comes from SetBranch + GetBranchRate
+    (src/treesub.c:3682, 3770-3811) -- the shim reads nodes[].branch after the reference's SetParameters."""
+    from paml_b200 import paml_io, simulate
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=200, seed=33, K=1) if prog == "baseml" else simulate.codon_m0_problem(ns=6, npatt=150, seed=41)
+
+    def write(d):
+        paml_io.write_pattern_files(p, d + "/s")
+        open(d + "/s.tre", "w").write("6 1\n((1,2),((3,4),(5,6)));\n")
+        if prog == "baseml":
+            with open(d + "/run.ctl", "w") as f:
+                f.write((T.BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=1, alpha="0", ncatG=1, nhomo=0, more=""))
+                        .replace("clock = 0", "clock = 1").replace("fix_blength = 1", "fix_blength = 0"))
+        else:
+            paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                     extra=dict(fix_kappa=0, fix_omega=0, fix_blength=0, clock=1))
+    T._close(T._both(tmp_path, prog, write, "mlb" if prog == "baseml" else "mlc"), 5e-6)
+
+
+def test_amino_acid_models(shim, tmp_path):
+    """aaml: Poisson (closed form, JC69-like) and an empirical matrix + gamma (eigenQaa once, src/codeml.c:2382-2383)."""
+    from paml_b200 import paml_io, simulate
+    wag = os.path.join(os.path.dirname(REFSRC), "dat", "wag.dat")
+    p = simulate.aa_gamma_problem(ns=7, npatt=150, seed=51, K=4)
+    for tag, extra in (("poisson", dict(model=0, fix_alpha=1, alpha=0, ncatG=1)),
+                       ("wag_gamma", dict(model=2, aaRatefile=wag, fix_alpha=0, alpha=0.5, ncatG=4))):
+        if tag == "wag_gamma" and not os.path.exists(wag):
+            continue
+
+        def write(d):
+            paml_io.write_pattern_files(p, d + "/s")
+            paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", seqtype=2, extra=dict(fix_blength=1, **extra))
+        (tmp_path / tag).mkdir()
+        T._close(T._both(tmp_path / tag, "codeml", write, "mlc"), 2e-6)
+
+
+def test_ambiguous_data_and_two_trees(shim, tmp_path):
+    """cleandata = 0 with gaps and ambiguity characters in the alignment (nChara / CharaMap), and a tree file with two trees:
+    the second tree must trigger a new upload of the topology (the shim's fingerprint of the static data)."""
+    import numpy as np
+    from paml_b200 import paml_io, simulate
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=200, seed=35, K=4)
+
+    def write(d):
+        ls = paml_io.write_sequence_files(p, d + "/s")
+        rng = np.random.default_rng(9)
+        lines = open(d + "/s.phy").read().splitlines()
+        out = [lines[0]]
+        for ln in lines[1:]:
+            name, seq = ln.split(None, 1)
+            seq = list(seq.strip())
+            for i in rng.choice(len(seq), len(seq) // 25, replace=False):
+                seq[i] = "-NRY?"[int(rng.integers(0, 5))]
+            out.append("%s  %s" % (name, "".join(seq)))
+        open(d + "/s.phy", "w").write("\n".join(out) + "\n")
+        open(d + "/s.tre", "w").write("6 2\n((1,2),(3,4),(5,6));\n((1,3),(2,4),(5,6));\n")
+        with open(d + "/run.ctl", "w") as f:
+            f.write((T.BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=0, alpha="0.5", ncatG=4, nhomo=0, more=""))
+                    .replace("cleandata = 1", "cleandata = 0").replace("fix_blength = 1", "fix_blength = 0"))
+    import re
+    vals = {}
+    for tag, exe in T._pair("baseml"):
+        d = tmp_path / tag
+        d.mkdir()
+        write(str(d))
+        T._run(exe, str(d))
+        vals[tag] = [float(v) for v in re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d / "mlb").read())]
+    assert len(vals["gpu"]) == len(vals["ref"]) == 2, vals
+    for a, b in zip(vals["gpu"], vals["ref"]):
+        assert abs(a - b) <= 2e-6 * abs(b), vals
+
+
+def test_two_data_sets(shim, tmp_path):
+    """ndata = 2: the driver re-reads a second alignment into the same globals; the shim must notice and upload it."""
+    import re
+    from paml_b200 import paml_io, simulate
+    p1 = simulate.codon_m0_problem(ns=6, npatt=120, seed=61)
+    p2 = simulate.codon_m0_problem(ns=6, npatt=120, seed=62)
+    vals = {}
+    for tag, exe in T._pair("codeml"):
+        d = tmp_path / tag
+        d.mkdir()
+        paml_io.write_sequence_files(p1, str(d / "a"))
+        paml_io.write_sequence_files(p2, str(d / "b"))
+        open(d / "s.phy", "w").write(open(d / "a.phy").read() + "\n" + open(d / "b.phy").read())
+        paml_io.write_codeml_ctl(str(d / "run.ctl"), "s.phy", "a.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, ndata=2))
+        T._run(exe, str(d))
+        vals[tag] = [float(v) for v in re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d / "mlc").read())]
+    assert len(vals["gpu"]) == len(vals["ref"]) == 2 and vals["ref"][0] != vals["ref"][1], vals
+    for a, b in zip(vals["gpu"], vals["ref"]):
+        assert abs(a - b) <= 2e-6 * abs(b), vals
