@@ -25,6 +25,7 @@ int lfunt_disp(double t, int a, int b, double xcom[], double *l, double space[])
 int lfuntdd_disp(double t, int a, int b, double xcom[], double *l, double *dl, double *ddl, double space[]);
 int lfunt_SiteClass_disp(double t, int a, int b, double xcom[], double *l, double space[]);
 int lfuntdd_SiteClass_disp(double t, int a, int b, double xcom[], double *l, double *dl, double *ddl, double space[]);
+int ConditionalPNode_disp(int inode, int igene, double x[]);
 #define lfun(a, b)   lfun_ref(a, b)
 #define lfundG(a, b) lfundG_ref(a, b)
 #define fx_r(a, b)   PBH_FXR_##a, b)
@@ -51,6 +52,13 @@ int lfuntdd_SiteClass_disp(double t, int a, int b, double xcom[], double *l, dou
 #define lfuntdd_SiteClass(a, b, c, d, e, f, g, h) PBH_LDS_##a, b, c, d, e, f, g, h)
 #define PBH_LDS_t      lfuntdd_SiteClass_disp(t
 #define PBH_LDS_double lfuntdd_SiteClass_ref(double
+/* ConditionalPNode: whole-tree calls `ConditionalPNode(tree.root, ..)` -> ConditionalPNode_disp; the definition, its own recursion
+   `ConditionalPNode(nodes[..].sons[i], ..)` and updateconP's `ConditionalPNode(inode, ..)` -> ConditionalPNode_ref */
+#define ConditionalPNode(a, b, c) PBH_CPN_##a, b, c)
+#define PBH_CPN_int   ConditionalPNode_ref(int
+#define PBH_CPN_nodes ConditionalPNode_ref(nodes
+#define PBH_CPN_inode ConditionalPNode_ref(inode
+#define PBH_CPN_tree  ConditionalPNode_disp(tree
 #define PBH_PW_void PatternWeight_ref(void)
 #define PBH_PW_     PatternWeight_b200()
 #include "baseml.c"
@@ -65,4 +73,5 @@ int lfuntdd_SiteClass_disp(double t, int a, int b, double xcom[], double *l, dou
 #undef lfuntdd
 #undef lfunt_SiteClass
 #undef lfuntdd_SiteClass
+#undef ConditionalPNode
 #include "plfun_b200.inc"

@@ -297,3 +297,37 @@ def test_two_data_sets(shim, tmp_path):
     assert len(vals["gpu"]) == len(vals["ref"]) == 2 and vals["ref"][0] != vals["ref"][1], vals
     for a, b in zip(vals["gpu"], vals["ref"]):
         assert abs(a - b) <= 2e-6 * abs(b), vals
+
+
+@pytest.mark.parametrize("which", ["beb_branch_site_A", "ancestors_method0", "ancestors_method1", "cpu_minbranches_refresh", "m0_ancestors_joint"])
+def test_whole_tree_conditional_p_node_through_the_abi(shim, tmp_path, monkeypatch, which):
+    """PB200_CPN=1: `ConditionalPNode(tree.root, ..)` called directly by BEB for branch-site models, by the ancestral
+    reconstruction and by the reference's own lfun / fx_r (host-vector refresh) is answered through pb200_cond_update +
+    pb200_cond_get, the vectors and scale factors copied back to nodes[].conP / com.nodeScaleF."""
+    monkeypatch.setenv("PB200_CPN", "1")
+    if which == "beb_branch_site_A":
+        test_labelled_branches(shim, tmp_path, "branch_site_A", dict(model=2, NSsites=2, ncatG=3), 0)
+        assert "Bayes Empirical Bayes" in open(tmp_path / "gpu" / "rst").read()
+        g, r = T._numbers(str(tmp_path / "gpu" / "rst")), T._numbers(str(tmp_path / "ref" / "rst"))
+        assert len(g) == len(r) and len(r) > 300
+        bad = [(a, b) for (a, da), (b, db) in zip(g, r) if abs(a - b) > 2e-3 + 2.5 * 10.0 ** (-min(da, db))]
+        assert not bad, bad[:10]
+    elif which == "ancestors_method0":
+        test_rates_for_sites_and_ancestors_method0(shim, tmp_path)
+    elif which == "ancestors_method1":
+        T.test_method1_ancestral_reconstruction_with_site_classes(tmp_path)
+    elif which == "cpu_minbranches_refresh":
+        T.test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path)
+    else:
+        from paml_b200 import paml_io, simulate
+        p = simulate.codon_m0_problem(ns=6, npatt=150, seed=83)
+
+        def write(d):
+            paml_io.write_sequence_files(p, d + "/s")
+            paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                     extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, RateAncestor=1))
+        dirs = _run_pair(shim, tmp_path, "codeml", write)
+        g, r = T._numbers(dirs["gpu"] + "/rst"), T._numbers(dirs["ref"] + "/rst")
+        assert len(g) == len(r) and len(r) > 300, (len(g), len(r))
+        bad = [(a, b) for (a, da), (b, db) in zip(g, r) if abs(a - b) > 2e-3 + 2.5 * 10.0 ** (-min(da, db))]
+        assert not bad, bad[:10]
