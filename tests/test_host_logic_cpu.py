@@ -331,3 +331,50 @@ def test_whole_tree_conditional_p_node_through_the_abi(shim, tmp_path, monkeypat
         assert len(g) == len(r) and len(r) > 300, (len(g), len(r))
         bad = [(a, b) for (a, da), (b, db) in zip(g, r) if abs(a - b) > 1e-2 + 2.5 * 10.0 ** (-min(da, db))]
         assert not bad, bad[:10]
+
+
+ZOO = [
+    ("codeml", "M7_beta", dict(NSsites=7, ncatG=5), False),
+    ("codeml", "M8_beta_w_BEB", dict(NSsites=8, ncatG=5), False),
+    ("codeml", "clade_model_C", dict(model=3, NSsites=2, ncatG=3), True),
+    ("codeml", "hkyREV", dict(hkyREV=1), False),
+    ("codeml", "codonfreq_F1x4", dict(CodonFreq=1), False),
+    ("codeml", "codonfreq_table", dict(CodonFreq=3), False),
+    ("codeml", "equal_codon_freqs", dict(CodonFreq=0), False),
+    ("codeml", "mito_code_60_states", dict(icode=1), False),
+    ("codeml", "m0_gamma_rates", dict(fix_alpha=0, alpha=0.7, ncatG=3), False),
+    ("baseml", "F81", dict(model=2), False),
+    ("baseml", "F84", dict(model=3), False),
+    ("baseml", "T92", dict(model=5), False),
+    ("baseml", "TN93_gamma", dict(model=6, fix_alpha=0, alpha="0.5", ncatG=4), False),
+    ("baseml", "JC69_gamma", dict(model=0, fix_alpha=0, alpha="0.5", ncatG=4), False),
+    ("baseml", "REV_estimated_pi", dict(model=7, nhomo=1), False),
+]
+
+
+@pytest.mark.parametrize("prog,tag,extra,labelled", ZOO, ids=[z[1] for z in ZOO])
+def test_model_zoo(shim, tmp_path, prog, tag, extra, labelled):
+    """Short fits over the model switches that change what SetParameters leaves in the globals the shim reads (codon frequency
+    models, genetic codes with n != 61, kappa parameterisations, beta / clade site classes, the TN93 family): the drop-in and the
+    reference must end at the same lnL."""
+    from paml_b200 import paml_io, simulate
+    if prog == "codeml":
+        p = simulate.codon_m0_problem(ns=6, npatt=90, seed=91)
+    else:
+        p = simulate.nuc_gtr_gamma_problem(ns=7, npatt=200, seed=92, K=4)
+
+    def write(d):
+        paml_io.write_sequence_files(p, d + "/s")
+        if labelled:
+            tre = open(d + "/s.tre").read()
+            i = tre.index("):")
+            open(d + "/s.tre", "w").write(tre[:i + 1] + " #1 " + tre[i + 1:])
+        if prog == "codeml":
+            paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                     extra=dict(dict(fix_kappa=0, fix_omega=0, fix_blength=1), **extra))
+        else:
+            kw = dict(Mgene=0, Malpha=0, model=4, fix_alpha=1, alpha="0", ncatG=1, nhomo=0, more="")
+            kw.update(extra)
+            with open(d + "/run.ctl", "w") as f:
+                f.write(T.BASEML_CTL % kw)
+    T._close(T._both(tmp_path, prog, write, "mlc" if prog == "codeml" else "mlb"), 1e-5)
