@@ -378,3 +378,22 @@ def test_model_zoo(shim, tmp_path, prog, tag, extra, labelled):
             with open(d + "/run.ctl", "w") as f:
                 f.write(T.BASEML_CTL % kw)
     T._close(T._both(tmp_path, prog, write, "mlc" if prog == "codeml" else "mlb"), 1e-5)
+
+
+@pytest.mark.parametrize("which", ["m0_fit", "m2a_neb_beb", "method1_m0", "genes", "whole_tree_cpn"])
+def test_pattern_shards_over_several_contexts(shim, tmp_path, monkeypatch, which):
+    """PB200_NGPU=3: the shim splits the patterns into contiguous shards (boundaries on multiples of 8), one context each, adds the
+    shards' -lnL (and, under method = 1, the derivatives of every Newton step), and reassembles per-pattern outputs (lnf, fhK,
+    resident vectors) in pattern order.  The mock ignores the device ordinal, so the bookkeeping is what is tested here."""
+    monkeypatch.setenv("PB200_NGPU", "3")
+    if which == "m0_fit":
+        D.test_codeml_m0_fit(tmp_path)
+    elif which == "m2a_neb_beb":
+        T.test_codeml_m2a_neb_beb_fixed_point(tmp_path)
+    elif which == "method1_m0":
+        T.test_method1_codeml_m0(tmp_path)
+    elif which == "genes":
+        T.test_baseml_genes(tmp_path, 4, 1)
+    else:
+        monkeypatch.setenv("PB200_CPN", "1")
+        test_rates_for_sites_and_ancestors_method0(shim, tmp_path)
