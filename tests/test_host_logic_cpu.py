@@ -188,15 +188,19 @@ def test_labelled_branches(shim, tmp_path, tag, extra, method):
     label), with the simultaneous optimiser and with method = 1 (where lfuntdd[_SiteClass] pick the set by the label of the
     branch under iteration): a foreground clade marked #1 in the tree file."""
     from paml_b200 import paml_io, simulate
-    p = simulate.codon_m0_problem(ns=8, npatt=(90 if "NSsites" in extra else 200), seed=45)
+    p = simulate.codon_m0_problem(ns=8, npatt=(60 if "NSsites" in extra else 200), seed=45)
 
     def write(d, m=method):
         paml_io.write_pattern_files(p, d + "/s")
         tre = open(d + "/s.tre").read()
         i = tre.index("):")
         open(d + "/s.tre", "w").write(tre[:i + 1] + " #1 " + tre[i + 1:])
+        fixed_point = (tag == "branch_site_A" and m == 0)     # one evaluation + NEB + BEB; the fit itself is what method = 1 covers
         paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
-                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=m, **extra))
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=(2 if fixed_point else 1), method=m, **extra))
+        if fixed_point:
+            with open(d + "/in.codeml", "w") as f:
+                f.write("-1  2.0  0.5 0.3  0.1 3.0\n")                 # kappa, p0 p1, w0 w2
     res = T._both(tmp_path, "codeml", write, "mlc")
     if method == 1:
         T._close_method1(res, "codeml", lambda d: write(d, 0), "mlc", tmp_path, rel=5e-6)
@@ -262,7 +266,7 @@ def test_ambiguous_data_and_two_trees(shim, tmp_path):
         open(d + "/s.phy", "w").write("\n".join(out) + "\n")
         open(d + "/s.tre", "w").write("6 2\n((1,2),(3,4),(5,6));\n((1,3),(2,4),(5,6));\n")
         with open(d + "/run.ctl", "w") as f:
-            f.write((T.BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=0, alpha="0.5", ncatG=4, nhomo=0, more=""))
+            f.write((T.BASEML_CTL % dict(Mgene=0, Malpha=0, model=4, fix_alpha=1, alpha="0", ncatG=1, nhomo=0, more=""))
                     .replace("cleandata = 1", "cleandata = 0").replace("fix_blength = 1", "fix_blength = 0"))
     import re
     vals = {}
@@ -359,7 +363,7 @@ def test_model_zoo(shim, tmp_path, prog, tag, extra, labelled):
     reference must end at the same lnL."""
     from paml_b200 import paml_io, simulate
     if prog == "codeml":
-        p = simulate.codon_m0_problem(ns=6, npatt=90, seed=91)
+        p = simulate.codon_m0_problem(ns=5, npatt=60, seed=91)
     else:
         p = simulate.nuc_gtr_gamma_problem(ns=7, npatt=200, seed=92, K=4)
 
