@@ -26,6 +26,7 @@ int lfuntdd_disp(double t, int a, int b, double xcom[], double *l, double *dl, d
 int lfunt_SiteClass_disp(double t, int a, int b, double xcom[], double *l, double space[]);
 int lfuntdd_SiteClass_disp(double t, int a, int b, double xcom[], double *l, double *dl, double *ddl, double space[]);
 int ConditionalPNode_disp(int inode, int igene, double x[]);
+void SetSeed_b200(int seed, int PrintSeed);
 #define lfun(a, b)   lfun_ref(a, b)
 #define lfundG(a, b) lfundG_ref(a, b)
 #define fx_r(a, b)   PBH_FXR_##a, b)
@@ -33,6 +34,7 @@ int ConditionalPNode_disp(int inode, int igene, double x[]);
 #define PBH_FXR_double fx_r_ref(double
 #define PatternWeight(a) PBH_PW_##a
 #define eigenQREV(a, b, c, d, e, f, g) eigenQREV_b200(a, b, c, d, e, f, g)
+#define SetSeed(a, b) SetSeed_b200(a, b)        /* tests only: PB200_TEST_SEED gives this program the reference run's starting values */
 /* method = 1: minbranches(xcom, ..), updateconP(x, ..), lfunt*(t, ..) calls -> ours; the definitions -> *_ref */
 #define minbranches(a, b) PBH_MB_##a, b)
 #define PBH_MB_xcom   minbranches_b200(xcom
@@ -67,6 +69,7 @@ int ConditionalPNode_disp(int inode, int igene, double x[]);
 #undef fx_r
 #undef PatternWeight
 #undef eigenQREV
+#undef SetSeed
 #undef minbranches
 #undef updateconP
 #undef lfunt

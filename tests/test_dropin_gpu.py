@@ -18,8 +18,14 @@ REF = os.path.join(REPO, "oracle", "_ref")
 
 
 def _run(exe, ctl, cwd, env=None):
+    base = dict(os.environ)
+    lib = os.path.join(REF, "libfixedseed.so")          # same random starting values for both programs (oracle/fixed_seed.c)
+    if os.path.exists(lib):
+        base.update(PB200_TEST_SEED="20261017")          # the drop-in derives the same seed itself (SetSeed wrapper in the shim)
+        if os.path.dirname(os.path.abspath(exe)) == os.path.abspath(REF):
+            base.update(LD_PRELOAD=lib)
     r = subprocess.run([exe, ctl], cwd=cwd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True, timeout=600, env=dict(os.environ, **(env or {})))
+                       text=True, timeout=600, env=dict(base, **(env or {})))
     assert r.returncode == 0, r.stdout[-2000:]
     return r.stdout
 

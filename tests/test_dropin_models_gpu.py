@@ -30,9 +30,23 @@ def _baseml_ctl(path, **kw):
         f.write(BASEML_CTL % d)
 
 
+def _same_start_env(exe=""):
+    """Both programs perturb their initial values with a generator seeded from /dev/urandom (SetSeed, src/tools.c:1378).  The
+    unmodified reference gets oracle/_ref/libfixedseed.so preloaded (test infrastructure, oracle/fixed_seed.c: fopen of
+    /dev/urandom answers with bytes derived from PB200_TEST_SEED); the drop-in derives the same seed from that variable in
+    its own SetSeed wrapper (plfun_b200.inc) and needs no preload.  So both start every fit at the same point."""
+    lib = os.path.join(REF, "libfixedseed.so")
+    if not os.path.exists(lib):
+        return dict(os.environ)
+    env = dict(os.environ, PB200_TEST_SEED="20261017")
+    if os.path.dirname(os.path.abspath(exe)) == os.path.abspath(REF):
+        env["LD_PRELOAD"] = lib
+    return env
+
+
 def _run(exe, cwd, ok=True):
     r = subprocess.run([exe, "run.ctl"], cwd=cwd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True, timeout=900)
+                       text=True, timeout=900, env=_same_start_env(exe))
     if ok:
         assert r.returncode == 0, r.stdout[-2000:]
     return r
@@ -161,7 +175,7 @@ def test_codeml_m3_five_classes_fixed_point(tmp_path):
         d.mkdir()
         write(str(d))
         r = subprocess.run([exe, "run.ctl"], cwd=str(d), stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                           text=True, timeout=900, env=dict(os.environ, PB200_EIGEN=mode))
+                           text=True, timeout=900, env=dict(_same_start_env(exe), PB200_EIGEN=mode))
         assert r.returncode == 0, r.stdout[-2000:]
         v = _lnl(str(d / "mlc"))
         assert abs(v - res["ref"][0]) <= 1e-9 * abs(res["ref"][0]), (mode, v, res["ref"][0])
@@ -225,7 +239,7 @@ def _fixed_start(path, ntime, tail):
 def _verbose_says_gpu(d, exe):
     """With PB200_VERBOSE the shim reports when minbranches stays on the reference's CPU routines: it must not."""
     r = subprocess.run([exe, "run.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True, timeout=900, env=dict(os.environ, PB200_VERBOSE="1"))
+                       text=True, timeout=900, env=dict(_same_start_env(exe), PB200_VERBOSE="1"))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "minbranches stays on the reference" not in r.stdout
 
@@ -319,7 +333,7 @@ def test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path):
         paml_io.write_codeml_ctl(str(d / "run.ctl"), "s.phy", "s.tre", kappa=2.0, omega=0.4,
                                  extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
         r = subprocess.run([exe, "run.ctl"], cwd=str(d), stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                           text=True, timeout=900, env=dict(os.environ, **env))
+                           text=True, timeout=900, env=dict(_same_start_env(exe), **env))
         assert r.returncode == 0, r.stdout[-2000:]
         v = _lnl(str(d / "mlc"))
         if ref is None:
