@@ -21,7 +21,7 @@ def _run(exe, ctl, cwd, env=None):
     base = dict(os.environ)
     lib = os.path.join(REF, "libfixedseed.so")          # same random starting values for both programs (oracle/fixed_seed.c)
     if os.path.exists(lib):
-        base.update(PB200_TEST_SEED="20261017")          # the drop-in derives the same seed itself (SetSeed wrapper in the shim)
+        base.update(PB200_TEST_SEED=os.environ.get("PB200_TEST_SEED", "20261017"))          # the drop-in derives the same seed itself (SetSeed wrapper in the shim)
         if os.path.dirname(os.path.abspath(exe)) == os.path.abspath(REF):
             base.update(LD_PRELOAD=lib)
     r = subprocess.run([exe, ctl], cwd=cwd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,

@@ -38,7 +38,7 @@ def _same_start_env(exe=""):
     lib = os.path.join(REF, "libfixedseed.so")
     if not os.path.exists(lib):
         return dict(os.environ)
-    env = dict(os.environ, PB200_TEST_SEED="20261017")
+    env = dict(os.environ, PB200_TEST_SEED=os.environ.get("PB200_TEST_SEED", "20261017"))
     if os.path.dirname(os.path.abspath(exe)) == os.path.abspath(REF):
         env["LD_PRELOAD"] = lib
     return env

@@ -71,7 +71,7 @@ def _fit_lnl(exe, d, env, outfile):
     base = dict(os.environ)
     lib = os.path.join(REPO, "oracle", "_ref", "libfixedseed.so")     # same random starting values in every run (oracle/fixed_seed.c)
     if os.path.exists(lib):
-        base.update(PB200_TEST_SEED="20261017")           # the drop-in seeds itself from it (SetSeed wrapper in the shim); no preload
+        base.update(PB200_TEST_SEED=os.environ.get("PB200_TEST_SEED", "20261017"))           # the drop-in seeds itself from it (SetSeed wrapper in the shim); no preload
     r = subprocess.run([exe, "run.ctl"], cwd=str(d), env=dict(base, **env), stdin=subprocess.DEVNULL,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
