@@ -25,9 +25,9 @@ endif
 $(BIN)/tools.o: $(REF)/tools.c
 	@mkdir -p $(BIN)
 	$(CC) -O3 -w -c -o $@ $<
-$(BIN)/codeml_b200: $(HOST)/codeml_b200.c $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
+$(BIN)/codeml_b200: $(HOST)/codeml_b200.c $(HOST)/wrap_b200.inc $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
 	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/codeml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
-$(BIN)/baseml_b200: $(HOST)/baseml_b200.c $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
+$(BIN)/baseml_b200: $(HOST)/baseml_b200.c $(HOST)/wrap_b200.inc $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
 	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/baseml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
 
 $(LIB): $(CSRC)/api.cu $(CSRC)/kernels.cuh $(CSRC)/patterns.cpp $(CSRC)/plan.cpp $(CSRC)/plan.h $(CSRC)/prune4.cuh $(CSRC)/prune4v2.cuh $(CSRC)/prune_tma.cuh $(CSRC)/eigen.cuh $(CSRC)/cond.cuh include/paml_b200.h

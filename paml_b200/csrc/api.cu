@@ -151,6 +151,7 @@ struct pb200_ctx {
     DevBuf d_peer_ptrs;
     bool p2p = false;
     unsigned long long eval_seq = 0;
+    unsigned long long p2p_timeout_ns = 20ull * 1000000000ull;   // PB200_P2P_TIMEOUT_MS: how long the fused all-reduce waits for a peer
 };
 
 static int ensure_host_stage(pb200_ctx* c, size_t bytes)
@@ -189,6 +190,8 @@ extern "C" int pb200_create(pb200_ctx** out, int device)
     CUDA_TRY(cudaMallocHost((void**)&c->h_result, 64));
     if (c->d_counter.ensure(64) || c->d_result.ensure(64)) return 1;
     CUDA_TRY(cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_result.p, 0, 64, c->stream));      // [0] -lnL, [1] status of the fused all-reduce (0 = ok)
+    memset(c->h_result, 0, 64);
     CUDA_TRY(cudaFuncSetAttribute(pt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 64 * 8));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -278,6 +281,7 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
         if (c->d_amb_mask.ensure(256)) return 1;
         CUDA_TRY(cudaMemcpy(c->d_amb_mask.p, mask.data(), 256, cudaMemcpyHostToDevice));
     }
+    if (ns != c->ns) { c->nnode = 0; c->root = -1; c->plan = Plan(); c->plan4 = Plan4(); }   // the plan was built for another tip count: pb200_set_tree must follow
     c->n = n; c->ns = ns; c->npatt = npatt; c->zstride = zstride; c->cleandata = cleandata; c->ncodes = ncodes;
     choose_shape(n, &c->NT, &c->KS);
     c->ld = 4 * c->KS;
@@ -373,7 +377,7 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
         c->zw_dirty = true;
     }
     static unsigned long long gen_counter = 0;
-    if (nnode != c->nnode) { c->cond_nclass = 0; c->csets.ok = false; }   // resident conditional vectors are laid out per node
+    c->cond_nclass = 0; c->csets.ok = false;               // resident conditional vectors belong to the previous topology
     c->plan = pl; c->nnode = nnode; c->root = root; c->plan_gen = ++gen_counter;
     c->have_eval = false;
     return 0;
@@ -794,6 +798,7 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         mp.tile_counter = (unsigned int*)c->d_counter.p + 4;
         mp.peer_xchg = (unsigned long long* const*)c->d_peer_ptrs.p;
         mp.nranks = c->p2p ? c->nranks : 1; mp.rank = c->rank; mp.seq = ++c->eval_seq;
+        mp.timeout_ns = c->p2p_timeout_ns;
         mp.result = (double*)c->d_result.p; mp.npatt = c->npatt; mp.nclass = L.nclass; mp.semantics = L.semantics;
         mp.nscale = c->plan.nscale;
         mix_kernel<<<L.mix_blocks, 256, 0, c->stream>>>(mp);
@@ -820,6 +825,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
                                 const double* pi)
 {
     if (!c) return fail("pb200_eval: null context");
+    if (c->pending) return fail("pb200_eval_begin: the previous evaluation of this context has not been collected (pb200_eval_end)");
     if (c->npatt == 0 || c->nnode == 0) return fail("pb200_eval: set_data and set_tree must be called first");
     if (semantics != SEM_LFUN && semantics != SEM_LFUNDG) return fail("pb200_eval: bad semantics");
     if (nclass < 1 || (semantics == SEM_LFUN && nclass != 1)) return fail("pb200_eval: bad nclass %d", nclass);
@@ -872,7 +878,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
         if (run_kernels(c, c->timing ? evs : nullptr)) return 1;
     }
     if (c->timing) CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_result, c->d_result.p, 16, cudaMemcpyDeviceToHost, c->stream));
     c->last_nclass = nclass;
     c->pending = true;
     return 0;
@@ -885,6 +891,16 @@ extern "C" int pb200_eval_end(pb200_ctx* c, double* neg_lnL)
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->pending = false;
+    if (c->h_result[1] != 0.0) {
+        // the fused NVLink all-reduce gave up waiting for a peer (mix_kernel): the sum is not valid
+        const int peer = (int)c->h_result[1] - 1;
+        cudaMemsetAsync(c->d_result.p, 0, 64, c->stream);
+        cudaStreamSynchronize(c->stream);
+        c->h_result[1] = 0.0;
+        *neg_lnL = c->h_result[0];
+        return fail("pb200_eval_end: rank %d's partial sum did not arrive within %.1f s (fused all-reduce, evaluation %llu); that rank "
+                    "died, stalled or is not evaluating", peer, 1e-9 * (double)c->p2p_timeout_ns, c->eval_seq);
+    }
     *neg_lnL = c->h_result[0];
     c->have_eval = true;
     if (c->timing) {
@@ -977,10 +993,13 @@ extern "C" int pb200_p2p_local_handle(pb200_ctx* c, char handle[64])
 {
     if (!c || !handle) return fail("pb200_p2p_local_handle: null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    if (!c->xchg) {
-        CUDA_TRY(cudaMalloc((void**)&c->xchg, 4096));
-        CUDA_TRY(cudaMemset(c->xchg, 0, 4096));
-    }
+    if (!c->xchg) CUDA_TRY(cudaMalloc((void**)&c->xchg, 4096));
+    // Cleared at every hand-shake, not only at allocation: pb200_p2p_init restarts the evaluation numbers at 0, and a
+    // (value, number) pair left by an earlier session must not be taken for a peer's new contribution.  Peers can only
+    // write here after pb200_p2p_init, i.e. after the launcher has gathered this handle from every rank.
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemset(c->xchg, 0, 4096));
+    CUDA_TRY(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, c->xchg));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -995,6 +1014,9 @@ extern "C" int pb200_p2p_init(pb200_ctx* c, int nranks, int rank, const char* ha
     if (!c->xchg) return fail("pb200_p2p_init: call pb200_p2p_local_handle first");
     CUDA_TRY(cudaSetDevice(c->device));
     std::vector<unsigned long long*> ptrs(nranks, nullptr);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < 64; r++)                                 // a re-initialisation: an IPC handle can be open only once per process
+        if (c->peer_map[r]) { cudaIpcCloseMemHandle(c->peer_map[r]); c->peer_map[r] = nullptr; }
     for (int r = 0; r < nranks; r++) {
         if (r == rank) { ptrs[r] = c->xchg; continue; }
         cudaIpcMemHandle_t h;
@@ -1008,6 +1030,10 @@ extern "C" int pb200_p2p_init(pb200_ctx* c, int nranks, int rank, const char* ha
     if (c->d_peer_ptrs.ensure((size_t)nranks * sizeof(void*))) return 1;
     CUDA_TRY(cudaMemcpy(c->d_peer_ptrs.p, ptrs.data(), (size_t)nranks * sizeof(void*), cudaMemcpyHostToDevice));
     c->nranks = nranks; c->rank = rank; c->p2p = true; c->eval_seq = 0;
+    {
+        const char* e = getenv("PB200_P2P_TIMEOUT_MS");
+        if (e && atof(e) > 0) c->p2p_timeout_ns = (unsigned long long)(atof(e) * 1e6);
+    }
     return 0;
 }
 
@@ -1077,8 +1103,6 @@ extern "C" int pb200_eigen_qrev(pb200_ctx* c, int n, int njob, const double* Q, 
     const size_t off_info = align16(off_sets + (size_t)njob * stride * 8), total = align16(off_info + (size_t)njob * 4);
     if (total > c->h_eig_cap) {
         if (c->h_eig) cudaFreeHost(c->h_eig);
-    if (c->h_cstage) cudaFreeHost(c->h_cstage);
-    if (c->h_cbr) cudaFreeHost(c->h_cbr);
         c->h_eig = nullptr; c->h_eig_cap = 0;
         CUDA_TRY(cudaMallocHost(&c->h_eig, total + total / 4));
         c->h_eig_cap = total + total / 4;

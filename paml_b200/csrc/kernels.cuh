@@ -747,7 +747,15 @@ struct MixParams {
     unsigned long long* const* peer_xchg;
     int nranks, rank;
     unsigned long long seq;   // evaluation number (> 0), doubles as the arrival flag
+    unsigned long long timeout_ns;   // a peer that has not arrived after this long is reported in result[1] (1 + its rank)
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Block b sums patterns [b*chunk, (b+1)*chunk) in a fixed order; the last block to finish adds the block
 // partials in index order.  No floating-point atomics anywhere, so -lnL(x) is reproducible call to call
@@ -817,9 +825,16 @@ __global__ void __launch_bounds__(256) mix_kernel(const MixParams p)
                 __threadfence_system();
                 dst[1] = p.seq;
                 volatile unsigned long long* src = p.peer_xchg[p.rank] + ((size_t)slot * p.nranks + tid) * 2;
-                while (src[1] != p.seq) { }
+                // bounded wait: a peer that died (or never launched) must not hang every GPU inside this kernel
+                const unsigned long long t0 = global_timer_ns();
+                bool arrived = true;
+                unsigned int spins = 0;
+                while (src[1] != p.seq) {
+                    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > p.timeout_ns) { arrived = false; break; }
+                }
                 __threadfence_system();
-                vals[tid] = __longlong_as_double((long long)src[0]);
+                vals[tid] = arrived ? __longlong_as_double((long long)src[0]) : __longlong_as_double(0x7ff8000000000000ll);
+                if (!arrived) p.result[1] = (double)(1 + tid);      // read by pb200_eval_end: fails loudly, naming the rank
             }
             __syncthreads();
             if (tid == 0) {

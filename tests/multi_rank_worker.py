@@ -40,8 +40,27 @@ if rank == 0:
     ref = whole.eval_problem(p)
     ok = abs(total - ref) <= 1e-12 * abs(ref) and abs(sum(parts) - ref) <= 1e-12 * abs(ref)
     ok = ok and all(abs(t - ref) <= 1e-12 * abs(ref) for t in totals_p2p) and len(set(totals_p2p)) == 1
-    print("MULTI_RANK_RESULT", world, total, ref, sum(parts), "OK" if ok else "MISMATCH")
     whole.close()
+# a peer that never arrives: the fused all-reduce must give up and the call must fail loudly (no hang inside the kernel).
+# New hand-shake (clears the exchange buffers, restarts the evaluation numbers) with a 300 ms limit; only rank 0 evaluates.
+os.environ["PB200_P2P_TIMEOUT_MS"] = "300"
+dist.barrier()
+handles = [None] * world
+dist.all_gather_object(handles, tl.p2p_local_handle())
+tl.p2p_init(world, rank, handles)
+again = tl.eval_problem(p)                      # everybody: still the right sum after the re-initialisation
+dist.barrier()
+timed_out = True
+if rank == 0:
+    from paml_b200.likelihood import PB200Error
+    try:
+        tl.eval_problem(p)
+        timed_out = False
+    except PB200Error as exc:
+        timed_out = "did not arrive" in str(exc)
+    ok = ok and timed_out and abs(again - ref) <= 1e-12 * abs(ref)
+    print("MULTI_RANK_RESULT", world, total, ref, sum(parts), "OK" if ok else "MISMATCH", "timeout-detected" if timed_out else "NO-TIMEOUT")
+dist.barrier()
 tl.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -115,3 +115,70 @@ def test_branch_function_rerooted(tl, path):
         tol2 = 1e-6 * max(1.0, abs(d2)) + 2 * abs(d2 - d2w) + 1e-12 * max(1.0, abs(out[1])) / e
         assert abs(out[1] - d1) <= tol1, (b, out[1], d1, tol1)
         assert abs(out[2] - d2) <= tol2, (b, out[2], d2, tol2)
+
+
+def test_eigen_batch_growth_between_branch_calls():
+    """Regression (round-1 ADVICE, high): pb200_eigen_qrev growing its pinned buffer used to free the pinned staging blocks of
+    pb200_cond_update / pb200_branch_lnl.  cond_update -> branch_lnl -> a larger eigen batch -> branch_lnl / cond_update on the
+    SAME context must keep giving the same numbers, and pb200_destroy must not double-free."""
+    p = load_fixture([f for f in GOLDEN if f.endswith("lysozyme_m0.pbfx")][0])
+    t = TreeLikelihood(0)
+    t.set_problem(p)
+    upd = _postorder(p, p.root, _sons(p))
+    t.cond_update(p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, upd, None)
+    b = int(p.sons[p.root, 0]); a = p.root
+    if b < p.ns:
+        b = [int(c) for c in p.sons[p.root, :p.nson[p.root]] if c >= p.ns][0]
+    # the branch b -> root from the vectors as they are: not the tree's likelihood (no rerooting), just a fixed function to repeat
+    args = (p.freqK, a, b, float(p.branch_t[0, b]), np.ones(1), p.branch_set[:, b], p.pi[:p.n], 0, True)
+    first = t.branch_lnl(*args)
+    n = p.n
+    s = p.set_data[0]
+    Root, U, V = s[:n], s[n:n + n * n].reshape(n, n), s[n + n * n:n + 2 * n * n].reshape(n, n)
+    Q = (U * Root[None, :]) @ V
+    pi = np.asarray(p.pi[:n], np.float64)
+    for njob in (1, 3, 17):                            # every call grows the solver's pinned mirror
+        R2, _, _, sw = t.eigen_qrev(np.tile(Q, (njob, 1, 1)), np.tile(pi, (njob, 1)))
+        assert (sw > 0).all() and np.abs(np.sort(R2[0]) - np.sort(Root)).max() < 1e-10
+        again = t.branch_lnl(*args)
+        assert (again == first).all(), (njob, first, again)
+        t.cond_update(p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, upd, None)
+        assert (t.branch_lnl(*args) == first).all()
+    t.close()
+
+
+def test_set_tree_invalidates_resident_vectors_and_begin_checks_pending():
+    """pb200_set_tree always drops the resident conditional vectors (they were computed for the previous topology, even one
+    with the same node count); pb200_set_data with another tip count requires a new pb200_set_tree; a second
+    pb200_eval_begin before pb200_eval_end is refused (the pinned staging block is still being read)."""
+    import ctypes as C
+    from paml_b200.likelihood import PB200Error, _ptr
+    p = load_fixture([f for f in GOLDEN if f.endswith("lysozyme_m0.pbfx")][0])
+    t = TreeLikelihood(0)
+    t.set_problem(p)
+    t.cond_update(p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, _postorder(p, p.root, _sons(p)), None)
+    t.cond_get(p.root)
+    t.set_tree(p.root, p.nson, p.sons, p.scale_flags if p.nscale else None)      # same tree again: still an invalidation
+    with pytest.raises(PB200Error):
+        t.cond_get(p.root)
+    b = int([c for c in p.sons[p.root, :p.nson[p.root]] if c >= p.ns][0])
+    with pytest.raises(PB200Error):
+        t.branch_lnl(p.freqK, p.root, b, 0.1, np.ones(1), p.branch_set[:, b], p.pi[:p.n], 0, True)
+    # begin twice
+    L = t._L
+    fk = np.ascontiguousarray(p.freqK, np.float64); sd = np.ascontiguousarray(p.set_data, np.float64)
+    bs = np.ascontiguousarray(p.branch_set, np.int32); bt = np.ascontiguousarray(p.branch_t, np.float64)
+    pi = np.ascontiguousarray(p.pi, np.float64)
+    args = (t._ctx, C.c_int(p.semantics), C.c_int(fk.shape[0]), _ptr(fk, C.c_double), C.c_int(p.set_kind), C.c_int(p.nr),
+            C.c_int(sd.shape[0]), C.c_longlong(sd.shape[1]), _ptr(sd, C.c_double), _ptr(bs, C.c_int), _ptr(bt, C.c_double),
+            _ptr(pi, C.c_double))
+    assert L.pb200_eval_begin(*args) == 0
+    assert L.pb200_eval_begin(*args) != 0 and b"not been collected" in L.pb200_last_error()
+    out = C.c_double(0)
+    assert L.pb200_eval_end(t._ctx, C.byref(out)) == 0
+    assert abs(out.value - p.ref_neg_lnL) <= 1e-11 * abs(p.ref_neg_lnL)
+    # other tip count without a new tree
+    z2 = np.ascontiguousarray(p.z[:p.ns - 1]); t.set_data(p.n, z2, p.fpatt, p.cleandata, p.nchara, p.charamap)
+    with pytest.raises(PB200Error):
+        t.eval_problem(p)
+    t.close()
