@@ -179,6 +179,8 @@ int pb200_set_timing(pb200_ctx *ctx, int enable);
 int pb200_last_timing(pb200_ctx *ctx, double ms[5]);
 /* Number of kernel launches this context has issued since creation. */
 long long pb200_launch_count(pb200_ctx *ctx);
+/* Name, template shape and launch geometry of the pruning kernel the last evaluation used ("" before the first). */
+const char *pb200_last_kernel(pb200_ctx *ctx);
 /* Host-side planner on its own (no GPU needed): the pruning "program" the kernel walks for this tree.
  * Writes up to cap ints to prog; returns the number of ints needed (negative on error) and the number
  * of on-chip slots (conditional-vector tiles live at once) in *nslots.                                   */

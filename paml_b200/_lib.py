@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libpaml_b200.so")
 SYMBOLS = [
     "pb200_create", "pb200_destroy", "pb200_last_error", "pb200_version", "pb200_set_data", "pb200_set_tree",
     "pb200_default_scale_flags", "pb200_eval", "pb200_eval_begin", "pb200_eval_end", "pb200_get_lnf", "pb200_get_fhK", "pb200_pmat",
-    "pb200_nccl_unique_id", "pb200_comm_init", "pb200_p2p_local_handle", "pb200_p2p_init", "pb200_p2p_enable", "pb200_set_timing", "pb200_last_timing", "pb200_launch_count",
+    "pb200_nccl_unique_id", "pb200_comm_init", "pb200_p2p_local_handle", "pb200_p2p_init", "pb200_p2p_enable", "pb200_set_timing", "pb200_last_timing", "pb200_launch_count", "pb200_last_kernel",
     "pb200_plan_tree", "pb200_plan_tree4", "pb200_measure_fp64_peak", "pb200_flush_l2", "pb200_bench_resident", "pb200_bench_e2e", "pb200_debug_set_program",
     "pb200_compress_patterns", "pb200_eigen_qrev", "pb200_cond_update", "pb200_branch_lnl", "pb200_cond_get",
 ]
@@ -35,6 +35,8 @@ def lib():
         L.pb200_version.restype = C.c_char_p
         L.pb200_launch_count.restype = C.c_longlong
         L.pb200_launch_count.argtypes = [C.c_void_p]
+        L.pb200_last_kernel.restype = C.c_char_p
+        L.pb200_last_kernel.argtypes = [C.c_void_p]
         L.pb200_destroy.argtypes = [C.c_void_p]
         L.pb200_destroy.restype = None
         _lib = L

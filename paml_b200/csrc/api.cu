@@ -135,6 +135,7 @@ struct pb200_ctx {
     void* h_eig = nullptr;      // its pinned mirror
     size_t h_eig_cap = 0;
     bool fused_last = false;    // the last pruning launch already produced lnf and the sum
+    char last_kernel[128] = "";  // name and launch shape of the last pruning kernel (pb200_last_kernel)
     void* h_stage = nullptr;
     size_t h_stage_cap = 0;
     double* h_result = nullptr;
@@ -510,6 +511,8 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     if (genv && atoi(genv) > 0) grid = atoi(genv);
     if (grid < 1) grid = 1;
     kfn<<<grid, warps * 32, smem, c->stream>>>(p);
+    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune_kernel<%d,%d,%d,%d,%s> grid %d x %d threads, %zu B smem", c->NT, c->KS,
+             L.rows / 8, L.max_warps, p.prog_in_const ? "true" : "false", grid, warps * 32, smem);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -598,6 +601,8 @@ static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const doubl
     // only if equal, otherwise fall back to the rounded size for both (source tiles are padded to it below)
     if (buf_stride != tile_bytes) return fail("internal: P(t) tile of %zu bytes is not a multiple of 128", tile_bytes);
     L.fn<<<grid, warps * 32, smem, c->stream>>>(pp);
+    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune_tma_kernel<%d,%d,%d,%d> grid %d x %d threads, %zu B smem", c->NT, c->KS,
+             L.rows / 8, L.max_warps, grid, warps * 32, smem);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -640,6 +645,7 @@ static int launch_prune4_t(pb200_ctx* c, int nclass, int semantics, const double
     long long cap = std::max<long long>(1, (long long)c->nsm * per_sm / std::max(1, nclass));
     dim3 grid((unsigned)std::min<long long>(want, std::max<long long>(cap, 1)), (unsigned)nclass);
     fn<<<grid, THREADS, smem, c->stream>>>(p);
+    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune4_kernel<%d,%d> grid %u x %u, %zu B smem", PPT, THREADS, grid.x, grid.y, smem);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -703,6 +709,7 @@ static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const doub
     if (genv && atoi(genv) > 0) cap = atoi(genv);
     dim3 grid((unsigned)std::min<long long>(want, cap), (unsigned)nclass);
     fn<<<grid, THREADS, smem, c->stream>>>(p);
+    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune4v2_kernel<%d,%d,%d> grid %u x %u, %zu B smem", PPT, THREADS, MINB, grid.x, grid.y, smem);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1060,6 +1067,7 @@ extern "C" int pb200_last_timing(pb200_ctx* c, double ms[5])
 }
 
 extern "C" long long pb200_launch_count(pb200_ctx* c) { return c ? c->launches : -1; }
+extern "C" const char* pb200_last_kernel(pb200_ctx* c) { return c ? c->last_kernel : ""; }
 
 extern "C" int pb200_measure_fp64_peak(pb200_ctx* c, double* dmma_tflops, double* dfma_tflops)
 {

@@ -50,6 +50,8 @@ class Problem:
     seqtype: int = -1
     model: int = -1
     nscale: int = 0
+    branch_len: np.ndarray = None  # float64 [nnode]: the tree's own branch lengths (synthetic problems; branch_t = these x class rate)
+    model_name: str = None
 
     @property
     def ninternal(self):

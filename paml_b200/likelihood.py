@@ -246,6 +246,9 @@ class TreeLikelihood:
     def launch_count(self):
         return int(self._L.pb200_launch_count(self._ctx))
 
+    def last_kernel(self):
+        return self._L.pb200_last_kernel(self._ctx).decode()
+
     def measure_fp64_peak(self):
         a, b = C.c_double(0), C.c_double(0)
         check(self._L.pb200_measure_fp64_peak(self._ctx, C.byref(a), C.byref(b)))

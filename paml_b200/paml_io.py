@@ -44,7 +44,7 @@ def write_pattern_files(p, prefix, h1=None, genes=None):
         f.write(" ".join("%d" % w for w in p.fpatt[:h1]))
         f.write("\n")
     with open(prefix + ".tre", "w") as f:
-        f.write("%d 1\n%s\n" % (p.ns, _tree_newick(p, p.branch_t[0])))
+        f.write("%d 1\n%s\n" % (p.ns, _tree_newick(p, p.branch_len if getattr(p, "branch_len", None) is not None else p.branch_t[0])))
     return h1
 
 
@@ -77,6 +77,18 @@ def write_codeml_ctl(path, seqfile, treefile, seqtype=1, model=0, NSsites=0, kap
                 CodonFreq=2, clock=0, model=model, NSsites=NSsites, icode=0, fix_kappa=1, kappa=kappa, fix_omega=1,
                 omega=omega, fix_alpha=1, alpha=0, ncatG=1, getSE=0, RateAncestor=0, Small_Diff=".5e-6",
                 cleandata=1, fix_blength=2, method=0)
+    keys.update(extra or {})
+    with open(path, "w") as f:
+        for k, v in keys.items():
+            f.write("%s = %s\n" % (k, v))
+
+
+def write_baseml_ctl(path, seqfile, treefile, model=7, alpha=0.5, ncatG=8, extra=None):
+    """A baseml control file with branch lengths taken from the tree file (fix_blength = 2) and alpha fixed; the
+    exchangeabilities of REV stay parameters -- fix them for a single evaluation with an `in.baseml` line `-1 a b c d e`."""
+    keys = dict(seqfile=seqfile, treefile=treefile, outfile="mlb", noisy=0, verbose=0, runmode=0, model=model, Mgene=0,
+                clock=0, fix_kappa=0, kappa=2, fix_alpha=1, alpha=alpha, Malpha=0, ncatG=ncatG, nhomo=0, getSE=0,
+                RateAncestor=0, Small_Diff="7e-6", cleandata=1, fix_blength=2, method=0)
     keys.update(extra or {})
     with open(path, "w") as f:
         for k, v in keys.items():

@@ -16,6 +16,11 @@ from . import _lib
 def compress_patterns(cols):
     """cols: uint8 [ns, nsites] (codes or raw characters).  Returns (z [ns, npatt], counts [npatt]) with
     patterns in ascending lexicographic (= strcmp) order of the column bytes."""
+    cols = np.ascontiguousarray(cols, np.uint8)
+    if cols.shape[1] > 50_000 and int(cols.max()) < 255:
+        # large inputs: the library's hash + sort (csrc/patterns.cpp, host code) gives the same order and counts far faster
+        r = pattern_weight(cols)
+        return r["z"], r["fpatt"].astype(np.int64)
     z, counts = np.unique(np.ascontiguousarray(cols.T), axis=0, return_counts=True)
     return np.ascontiguousarray(z.T), counts
 

@@ -26,13 +26,12 @@ def evolve(tree, pmat_of_branch, pi, nsites, rng):
             P = pmat_of_branch(c)
             cdf = np.cumsum(P, axis=1)
             cdf /= cdf[:, -1:]
-            u = rng.random(nsites)
-            par = states[v]
-            child = np.zeros(nsites, np.uint8)
-            for s in range(n):
-                idx = np.nonzero(par == s)[0]
-                if idx.size:
-                    child[idx] = np.minimum(np.searchsorted(cdf[s], u[idx], side="right"), n - 1)
+            # one sorted table for all parent states: entry s*n + j = s + cdf[s, j]; the child of a site with parent s and
+            # uniform u is the number of entries of row s that are <= u, i.e. searchsorted(table, s + u) - s*n
+            table = (np.arange(n)[:, None] + cdf).ravel()
+            par = states[v].astype(np.int64)
+            key = par + rng.random(nsites)
+            child = np.minimum(np.searchsorted(table, key, side="right") - par * n, n - 1).astype(np.uint8)
             states[c] = child
             order.append(c)
     return states[:tree.ns]
@@ -44,6 +43,7 @@ def _finish(p, tree, every):
     p.nscale, p.scale_flags = default_scale_flags(tree.nnode, tree.root, tree.nson, tree.sons, every)
     p.nchara, p.charamap = default_ambiguity_maps(p.n)
     p.cleandata = 1
+    p.branch_len = tree.branch.copy()        # the tree's own branch lengths (branch_t carries them times the class rates)
     return p
 
 
@@ -54,6 +54,24 @@ def _patterns(z_sites, npatt, rng, n):
     if z.shape[1] >= npatt:
         return z[:, :npatt].copy(), w[:npatt].astype(float)
     return z, w.astype(float)
+
+
+def _grow_patterns(npatt, first_sites, make_sites, rng, n, rounds=10):
+    """Simulate until `npatt` distinct site patterns exist (the first npatt are kept, weights = counts): make_sites(k)
+    returns k more simulated sites [ns, k].  Discrete-gamma and low-omega classes yield many constant sites, so the
+    number of sites needed is not known in advance."""
+    z = None; w = None
+    k = first_sites
+    for _ in range(rounds):
+        zs = make_sites(k)
+        if z is not None:
+            zs = np.concatenate([np.repeat(z, w.astype(np.int64), axis=1), zs], axis=1)
+        z, w = _patterns(zs, npatt, rng, n)
+        if z.shape[1] >= npatt:
+            break
+        got = max(1, z.shape[1])
+        k = int((npatt - got) * max(1.3, 1.15 * zs.shape[1] / got)) + 64       # the shortfall at the yield seen so far
+    return z, w
 
 
 def codon_m0_problem(ns=8, npatt=100_000, seed=13147, kappa=5.0, omega=0.3, newick=None, bl=(0.05, 0.3), sim_factor=2.2):
@@ -118,13 +136,15 @@ def codon_sites_problem(ns=32, npatt=50_000, seed=13149, kappa=2.0, freqs=(0.6, 
     Qf = sum(f * r[3] for f, r in zip(freqs, raw))
     for Root, U, V, mr in raw:
         sets.append(models.uvroot_set(Root / Qf, U, V))
-    site_cls = rng.choice(K, size=int(npatt * 1.6), p=freqs)
-    zs = np.zeros((tree.ns, site_cls.size), np.uint8)
-    for k in range(K):
-        idx = np.nonzero(site_cls == k)[0]
-        Root, U, V, mr = raw[k]
-        zs[:, idx] = evolve(tree, lambda c: models.pmat_uvroot(tree.branch[c], Root / Qf, U, V), pi, idx.size, rng)
-    z, w = _patterns(zs, npatt, rng, 61)
+    def make_sites(nsites):
+        site_cls = rng.choice(K, size=nsites, p=freqs)
+        zs = np.zeros((tree.ns, site_cls.size), np.uint8)
+        for k in range(K):
+            idx = np.nonzero(site_cls == k)[0]
+            Root, U, V, mr = raw[k]
+            zs[:, idx] = evolve(tree, lambda c: models.pmat_uvroot(tree.branch[c], Root / Qf, U, V), pi, idx.size, rng)
+        return zs
+    z, w = _grow_patterns(npatt, int(npatt * 1.6), make_sites, rng, 61)
     p = Problem(program=1, n=61, npatt=z.shape[1], z=z, fpatt=w, pi=pi, semantics=SEM_LFUNDG, nclass=K,
                 freqK=freqs, set_kind=KIND_UVROOT, nr=61, nset=K)
     p.set_data = np.stack(sets); p.set_stride = p.set_data.shape[1]
@@ -156,18 +176,37 @@ def _codon_raw(kappa, omega, pi):
     return Root * mr, U, V, mr
 
 
-def aa_gamma_problem(ns=64, npatt=200_000, seed=13151, alpha=0.5, K=4, bl=(0.02, 0.2)):
-    """BASELINE config 4 shape: aaml empirical-matrix model + discrete gamma (K classes share one set, t*rK)."""
+def wag_model():
+    """The WAG model (dat/wag.dat) in spectral form, exactly as the reference's eigenQaa left it: read from the golden fixture
+    tests/golden/stewart_wag_g4.pbfx (dumped from the unmodified reference running aaml with aaRatefile = wag.dat, model = 2,
+    i.e. WAG's own frequencies).  Returns None when the fixture is not there."""
+    import os
+    from .fixture import load_fixture
+    f = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "stewart_wag_g4.pbfx")
+    if not os.path.exists(f):
+        return None
+    q = load_fixture(f)
+    n = 20
+    sd = np.asarray(q.set_data).reshape(-1)
+    return sd[:n].copy(), sd[n:n + n * n].reshape(n, n).copy(), sd[n + n * n:n + 2 * n * n].reshape(n, n).copy(), np.asarray(q.pi[:n], float).copy()
+
+
+def aa_gamma_problem(ns=64, npatt=200_000, seed=13151, alpha=0.5, K=4, bl=(0.02, 0.2), wag=False):
+    """BASELINE config 4 shape: aaml empirical-matrix model + discrete gamma (K classes share one set, t*rK).
+    wag=True: the WAG matrix of dat/wag.dat (see wag_model); otherwise a seeded random reversible 20-state model."""
     rng = np.random.default_rng(seed)
     tree = random_tree(ns, seed, bl[0], bl[1])
-    Root, U, V, pi = models.synthetic_aa_model()
+    m = wag_model() if wag else None
+    Root, U, V, pi = m if m is not None else models.synthetic_aa_model()
     freqK, rK = models.discrete_gamma(alpha, K)
-    site_cls = rng.integers(0, K, size=int(npatt * 1.02) + 64)
-    zs = np.zeros((tree.ns, site_cls.size), np.uint8)
-    for k in range(K):
-        idx = np.nonzero(site_cls == k)[0]
-        zs[:, idx] = evolve(tree, lambda c: models.pmat_uvroot(tree.branch[c] * rK[k], Root, U, V), pi, idx.size, rng)
-    z, w = _patterns(zs, npatt, rng, 20)
+    def make_sites(nsites):
+        site_cls = rng.integers(0, K, size=nsites)
+        zs = np.zeros((tree.ns, site_cls.size), np.uint8)
+        for k in range(K):
+            idx = np.nonzero(site_cls == k)[0]
+            zs[:, idx] = evolve(tree, lambda c: models.pmat_uvroot(tree.branch[c] * rK[k], Root, U, V), pi, idx.size, rng)
+        return zs
+    z, w = _grow_patterns(npatt, int(npatt * 1.02) + 64, make_sites, rng, 20)
     p = Problem(program=1, n=20, npatt=z.shape[1], z=z, fpatt=w, pi=pi, semantics=SEM_LFUNDG, nclass=K,
                 freqK=freqK, set_kind=KIND_UVROOT, nr=20, nset=1)
     p.set_data = models.uvroot_set(Root, U, V).reshape(1, -1); p.set_stride = p.set_data.shape[1]
@@ -175,6 +214,7 @@ def aa_gamma_problem(ns=64, npatt=200_000, seed=13151, alpha=0.5, K=4, bl=(0.02,
     p.branch_set = np.zeros((K, tree.nnode), np.int32); p.branch_set[:, tree.root] = -1
     p.branch_t = rK[:, None] * tree.branch[None, :]
     p.seqtype = 2
+    p.model_name = "WAG (dat/wag.dat)" if m is not None else "seeded random reversible 20-state model"
     return p
 
 
@@ -190,12 +230,14 @@ def nuc_gtr_gamma_problem(ns=128, npatt=1_000_000, seed=1234567, alpha=0.5, K=8,
     def P(t):
         M = (Cijk * np.expm1(t * Root)[None, None, :]).sum(-1) + np.eye(4)
         return np.maximum(M, 0)
-    site_cls = rng.integers(0, K, size=int(npatt * 1.05) + 64)
-    zs = np.zeros((tree.ns, site_cls.size), np.uint8)
-    for k in range(K):
-        idx = np.nonzero(site_cls == k)[0]
-        zs[:, idx] = evolve(tree, lambda c: P(tree.branch[c] * rK[k]), pi, idx.size, rng)
-    z, w = _patterns(zs, npatt, rng, 4)
+    def make_sites(nsites):
+        site_cls = rng.integers(0, K, size=nsites)
+        zs = np.zeros((tree.ns, site_cls.size), np.uint8)
+        for k in range(K):
+            idx = np.nonzero(site_cls == k)[0]
+            zs[:, idx] = evolve(tree, lambda c: P(tree.branch[c] * rK[k]), pi, idx.size, rng)
+        return zs
+    z, w = _grow_patterns(npatt, int(npatt * 1.36) + 64, make_sites, rng, 4)
     p = Problem(program=0, n=4, npatt=z.shape[1], z=z, fpatt=w, pi=pi, semantics=SEM_LFUNDG, nclass=K,
                 freqK=freqK, set_kind=KIND_CIJK, nr=nr, nset=1)
     p.set_data = cset.reshape(1, -1); p.set_stride = p.set_data.shape[1]

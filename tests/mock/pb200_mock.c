@@ -312,6 +312,7 @@ int pb200_p2p_enable(pb200_ctx *c, int enable) { (void)c; (void)enable; return f
 int pb200_set_timing(pb200_ctx *c, int enable) { (void)c; (void)enable; return 0; }
 int pb200_last_timing(pb200_ctx *c, double ms[5]) { (void)c; memset(ms, 0, 5 * sizeof(double)); return 0; }
 long long pb200_launch_count(pb200_ctx *c) { return c ? c->launches : -1; }
+const char *pb200_last_kernel(pb200_ctx *c) { return "mock (CPU oracle, tests only)"; }
 int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons, const unsigned char *scale_flags, int *prog, int cap, int *nslots)
 { (void)nnode; (void)ns; (void)root; (void)nson; (void)sons; (void)maxsons; (void)scale_flags; (void)prog; (void)cap; (void)nslots; return -1; }
 int pb200_plan_tree4(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons, const unsigned char *scale_flags, int *ops, int cap_ops,

@@ -140,15 +140,36 @@ def test_shards_add_up(tl):
     assert abs(parts - whole) <= 1e-12 * abs(whole)
 
 
-def test_full_size_properties(tl):
-    """BASELINE config 2 at full size (8 taxa, 61 states, 1e5 patterns): too slow for the scalar oracle in a
-    unit test, so check size-independent properties: (i) doubling every weight doubles -lnL exactly,
-    (ii) a random subsample of patterns agrees with the oracle per pattern, (iii) shards sum to the whole."""
+def _full_size(cfg):
+    if cfg == "cfg2":
+        return simulate.codon_m0_problem(npatt=100_000, seed=13147)
+    if cfg == "cfg3_K4":
+        return simulate.codon_sites_problem(ns=32, npatt=50_000, seed=13149, freqs=(0.4, 0.3, 0.2, 0.1), omegas=(0.05, 0.3, 1.0, 2.5))
+    if cfg == "cfg3_K3":
+        return simulate.codon_sites_problem(ns=32, npatt=50_000, seed=13149, freqs=(0.6, 0.3, 0.1), omegas=(0.1, 1.0, 2.5))
+    if cfg == "cfg4":
+        return simulate.aa_gamma_problem(ns=64, npatt=200_000, seed=13151, wag=True)
+    if cfg == "cfg5":
+        return simulate.nuc_gtr_gamma_problem(ns=128, npatt=1_000_000, seed=1234567)
+    raise ValueError(cfg)
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3_K3", "cfg3_K4", "cfg4", "cfg5"])
+def test_full_size_properties(tl, cfg):
+    """Every BASELINE configuration AT ITS STATED SIZE (cfg2: 8 taxa x 1e5 codon patterns; cfg3: 32 taxa x 5e4 codon patterns,
+    3 and 4 site classes; cfg4: 64 taxa x 2e5 amino-acid patterns, WAG + 4 gamma classes; cfg5: 128 taxa x 1e6 nucleotide
+    patterns, GTR + 8 gamma classes).  The scalar oracle is too slow for a whole evaluation at these sizes in a unit test, so
+    the checks are size-independent properties: (i) -lnL equals the weighted sum of the per-pattern values, (ii) doubling every
+    weight doubles -lnL exactly, (iii) a random 3 000-pattern subsample agrees with the oracle per pattern AND per class,
+    (iv) three ragged shards sum to the whole."""
     from oracle import oracle
-    p = simulate.codon_m0_problem(npatt=100_000, seed=13147)
+    p = _full_size(cfg)
+    want = dict(cfg2=100_000, cfg3_K3=50_000, cfg3_K4=50_000, cfg4=200_000, cfg5=1_000_000)[cfg]
+    assert p.npatt == want, (cfg, p.npatt)
     tl.set_problem(p)
     v = tl.eval_problem(p)
     lnf = tl.lnf()
+    fhK = tl.fhK() if p.nclass > 1 else None
     assert np.isfinite(v) and (lnf < 0).all()
     assert abs(-(lnf * p.fpatt).sum() - v) <= 1e-12 * abs(v)
     q = simulate.Problem(**{k: getattr(p, k) for k in p.__dataclass_fields__})
@@ -160,6 +181,19 @@ def test_full_size_properties(tl):
     s.z = p.z[:, idx].copy(); s.fpatt = p.fpatt[idx].copy(); s.npatt = len(idx)
     r = oracle.lnl(s)
     np.testing.assert_allclose(lnf[idx], r["lnf"], rtol=0, atol=ABS_LNF)
+    if fhK is not None:
+        _check_fhK(fhK[:, idx], r["fhK"], p.nscale > 0)
+    # the subsample's own total against the oracle's: the north-star tolerance is 1e-6 relative, the bar here 1e-11
+    tl.set_problem(s)
+    vs = tl.eval_problem(s)
+    assert abs(vs - r["neg_lnL"]) <= REL_LNL * abs(r["neg_lnL"])
+    # ragged shards (boundaries not multiples of the tile sizes) add up to the whole
+    cuts = [0, p.npatt // 3 + 5, 2 * p.npatt // 3 - 3, p.npatt]
+    parts = 0.0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        tl.set_problem(p, a, b)
+        parts += tl.eval_problem(p)
+    assert abs(parts - v) <= 1e-12 * abs(v)
 
 
 def test_errors_are_loud(tl):
