@@ -232,6 +232,8 @@ def test_amino_acid_models(shim, tmp_path):
     """aaml: Poisson (closed form, JC69-like) and an empirical matrix + gamma (eigenQaa once, src/codeml.c:2382-2383)."""
     from paml_b200 import paml_io, simulate
     wag = os.path.join(os.path.dirname(REFSRC), "dat", "wag.dat")
+    if not os.path.exists(wag):                          # GPU box: the copy that travels with the reference binaries
+        wag = os.path.join(REPO, "oracle", "_ref", "dat", "wag.dat")
     p = simulate.aa_gamma_problem(ns=7, npatt=150, seed=51, K=4)
     for tag, extra in (("poisson", dict(model=0, fix_alpha=1, alpha=0, ncatG=1)),
                        ("wag_gamma", dict(model=2, aaRatefile=wag, fix_alpha=0, alpha=0.5, ncatG=4))):
