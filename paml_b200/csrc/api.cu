@@ -691,14 +691,56 @@ static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const doub
     p.zw = (const unsigned int*)c->d_zw.p; p.zwstride = c->zstride; p.npatt = c->npatt; p.ngroups = ngroups;
     p.P = (const double*)c->d_P.p; p.pstride = (int)c->pstride; p.nnode = c->nnode; p.nclass = nclass; p.nslots = pl.nslots;
     p.semantics = semantics; p.nscale = c->plan.nscale; p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
+    p.ns = c->ns; p.cls0 = 0; p.cp_class_stride = 0; p.cp_base = 0;
     const size_t slot_bytes = (size_t)pl.nslots * PPT * 2 * THREADS * sizeof(double2);
+    // Internal branches' matrices through the constant cache (uniform operands): needs the op words in constant memory too
+    // (their node fields must be provably warp-uniform) and room for at least one class in c_P4.  PB200_NUC_PCONST=0: off.
+    const int per_class = (c->nnode - c->ns) * 16;          // dense 4x4 blocks in c_P4
+    const char* pcenv = getenv("PB200_NUC_PCONST");
+    int cls_per_launch = (in_const && per_class > 0 && !(pcenv && atoi(pcenv) == 0)) ? PB200_CONST_P4_DOUBLES / per_class : 0;
+    const size_t tip_bytes = (size_t)c->ns * c->pstride * sizeof(double);
+    if (cls_per_launch > 0 && slot_bytes + tip_bytes > (size_t)200 * 1024) cls_per_launch = 0;
+    if (cls_per_launch > 0) {
+        const char* genv = getenv("PB200_NUC_CLS_PER_LAUNCH");
+        if (genv && atoi(genv) > 0) cls_per_launch = std::min(cls_per_launch, atoi(genv));
+        cls_per_launch = std::min(cls_per_launch, nclass);
+        const size_t smem = slot_bytes + tip_bytes;
+        void (*fn)(const Prune4v2Params) = prune4v2_kernel<PPT, THREADS, MINB, true, true, true>;
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long long want = (c->npatt + (long long)THREADS * PPT - 1) / ((long long)THREADS * PPT);
+        p.cp_class_stride = per_class; p.cp_base = -16 * c->ns;
+        double* cp4 = nullptr;
+        CUDA_TRY(cudaGetSymbolAddress((void**)&cp4, c_P4));
+        for (int c0 = 0; c0 < nclass; c0 += cls_per_launch) {
+            const int ncl = std::min(cls_per_launch, nclass - c0);
+            for (int k = 0; k < ncl; k++)            // stream-ordered: the previous launch has finished reading c_P4
+                CUDA_TRY(cudaMemcpy2DAsync(cp4 + (size_t)k * per_class, 16 * sizeof(double),
+                                           (const double*)c->d_P.p + ((size_t)(c0 + k) * c->nnode + c->ns) * c->pstride,
+                                           (size_t)c->pstride * sizeof(double), 16 * sizeof(double), (size_t)(c->nnode - c->ns),
+                                           cudaMemcpyDeviceToDevice, c->stream));
+            long long cap = std::max<long long>(1, (long long)c->nsm * per_sm / ncl);
+            const char* genv2 = getenv("PB200_GRID");
+            if (genv2 && atoi(genv2) > 0) cap = atoi(genv2);
+            dim3 grid((unsigned)std::min<long long>(want, cap), (unsigned)ncl);
+            p.cls0 = c0;
+            fn<<<grid, THREADS, smem, c->stream>>>(p);
+            snprintf(c->last_kernel, sizeof(c->last_kernel), "prune4v2_kernel<%d,%d,%d,PCONST> %d launch(es) of grid %u x %u, %zu B smem", PPT,
+                     THREADS, MINB, (nclass + cls_per_launch - 1) / cls_per_launch, grid.x, grid.y, smem);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        return 0;
+    }
     const size_t p_bytes = (size_t)c->nnode * c->pstride * sizeof(double);
     const bool psm = slot_bytes + p_bytes <= (size_t)(MINB >= 2 ? 100 : 200) * 1024;
     const size_t smem = slot_bytes + (psm ? p_bytes : 0);
     if (smem > (size_t)227 * 1024) return fail("4-state kernel: %d parked slots do not fit in shared memory", pl.nslots);
     void (*fn)(const Prune4v2Params) =
-        psm ? (in_const ? prune4v2_kernel<PPT, THREADS, MINB, true, true> : prune4v2_kernel<PPT, THREADS, MINB, true, false>)
-            : (in_const ? prune4v2_kernel<PPT, THREADS, MINB, false, true> : prune4v2_kernel<PPT, THREADS, MINB, false, false>);
+        psm ? (in_const ? prune4v2_kernel<PPT, THREADS, MINB, true, true, false> : prune4v2_kernel<PPT, THREADS, MINB, true, false, false>)
+            : (in_const ? prune4v2_kernel<PPT, THREADS, MINB, false, true, false> : prune4v2_kernel<PPT, THREADS, MINB, false, false, false>);
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, smem));
@@ -724,7 +766,6 @@ static int launch_prune4v2(pb200_ctx* c, int nclass, int semantics, const double
     if (v == 21) return launch_prune4v2_t<2, 128, 4>(c, nclass, semantics, d_pi);
     if (v == 3) return launch_prune4v2_t<3, 128, 3>(c, nclass, semantics, d_pi);
     if (v == 23) return launch_prune4v2_t<2, 384, 2>(c, nclass, semantics, d_pi);
-    if (v == 27) return launch_prune4v2_t<2, 768, 1>(c, nclass, semantics, d_pi);
     if (v == 13) return launch_prune4v2_t<1, 512, 2>(c, nclass, semantics, d_pi);
     return launch_prune4v2_t<2, 256, 2>(c, nclass, semantics, d_pi);
 }

@@ -255,8 +255,13 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
 // ------------------------------------------------------------------------------------------------
 // The pruning program of the tree in use: every warp reads it uniformly, op after op, on its critical path,
 // so it lives in constant memory (uniform loads through the constant cache) when it fits.
-#define PB200_CONST_PROG_INTS 12288
+#define PB200_CONST_PROG_INTS 6144
 __constant__ int c_prog[PB200_CONST_PROG_INTS];
+// The 4x4 P(t) of the internal branches of the 4-state kernel (prune4v2.cuh, PCONST): warp-uniform operands, read through
+// the constant cache into uniform registers (LDCU) and fed to DFMA as uniform operands -- they never pass the LSU.
+// c_prog + c_P4 = 24 KB + 40 KB of the 64 KB constant bank.
+#define PB200_CONST_P4_DOUBLES 5120
+__constant__ double c_P4[PB200_CONST_P4_DOUBLES];
 
 struct PruneParams {
     const int* prog;            // plan.h program in global memory (used when it does not fit c_prog)

@@ -29,6 +29,10 @@ struct Prune4v2Params {
     int nnode, nclass, nslots, semantics, nscale;
     const double* pi;           // [>=4]
     double* fhK;                // [nclass][npatt]
+    // PCONST: the internal branches' matrices of classes cls0 .. cls0 + gridDim.y - 1 sit in c_P4 as dense 4x4 blocks (16
+    // doubles each): class blockIdx.y, node v (>= ns) at cp_base + blockIdx.y * cp_class_stride + 16 v  (cp_base = -16 ns);
+    // shared memory then holds only the tip matrices
+    int ns, cls0, cp_class_stride, cp_base;
 };
 
 // walk-ordered packing: zw[g][h] = codes of tips tip_order[4g..4g+3] at pattern h (missing tips: 0)
@@ -66,26 +70,29 @@ __device__ __forceinline__ void sts_f64x2(unsigned int addr, double a, double b)
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(addr), "d"(a), "d"(b) : "memory");
 }
 
-template <int PPT, int THREADS, int MINB, bool PSM, bool CP>
+template <int PPT, int THREADS, int MINB, bool PSM, bool CP, bool PCONST>
 __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2Params p)
 {
     extern __shared__ __align__(16) double sm4v2[];
     const int tid = threadIdx.x;
-    const int cls = blockIdx.y;
+    const int cls = p.cls0 + blockIdx.y;
     const long long N = p.npatt;
     const int pstride = p.pstride;
     const unsigned int pstride_b = (unsigned int)pstride * 8u;
     const double* Pg = p.P + (size_t)cls * p.nnode * pstride;
+    // matrices staged in shared memory: all of the class's (PSM) or, when the internal branches' are in c_P4, the tips' only
+    // (tips are nodes 0 .. ns-1: the first ns matrices)
+    const int nstaged = PCONST ? p.ns : p.nnode;
     if (PSM) {
         const double2* src = reinterpret_cast<const double2*>(Pg);
         double2* dst = reinterpret_cast<double2*>(sm4v2);
-        for (int e = tid; e < p.nnode * pstride / 2; e += THREADS) dst[e] = src[e];
+        for (int e = tid; e < nstaged * pstride / 2; e += THREADS) dst[e] = src[e];
         __syncthreads();
     }
-    // shared-memory byte addresses: the class's matrices [nnode][pstride] (if PSM), then the parked slots
+    // shared-memory byte addresses: the staged matrices [nstaged][pstride] (if PSM), then the parked slots
     // [nslots][PPT][2][THREADS] x 16 bytes
     const unsigned int smem0 = (unsigned int)__cvta_generic_to_shared(sm4v2);
-    const unsigned int slot0 = smem0 + (PSM ? (unsigned int)p.nnode * pstride_b : 0u) + (unsigned int)tid * 16u;
+    const unsigned int slot0 = smem0 + (PSM ? (unsigned int)nstaged * pstride_b : 0u) + (unsigned int)tid * 16u;
     constexpr unsigned int SLOT_BYTES = PPT * 2 * THREADS * 16;
     const double pi0 = p.pi[0], pi1 = p.pi[1], pi2 = p.pi[2], pi3 = p.pi[3];
     const int nops = p.nops, ngroups = p.ngroups;
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
     for (long long base = (long long)blockIdx.x * THREADS * PPT; base < N; base += (long long)gridDim.x * THREADS * PPT) {
         long long h[PPT];
         const unsigned int* zp[PPT];
-        unsigned int cw[PPT], r[PPT][4];                 // current code word; ring of the next four (word g lives in r[g & 3])
+        unsigned int cw[PPT], r[PPT][4];                 // current code word; queue of the next four (r[0] is the next one)
 #pragma unroll
         for (int u = 0; u < PPT; u++) {
             h[u] = base + (long long)u * THREADS + tid;
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             zp[u] = p.zw + hc;
             cw[u] = __ldg(zp[u]);
 #pragma unroll
-            for (int d = 1; d <= 4; d++) r[u][d & 3] = (d < ngroups) ? __ldg(zp[u] + (size_t)d * zws) : 0u;
+            for (int d = 1; d <= 4; d++) r[u][d - 1] = (d < ngroups) ? __ldg(zp[u] + (size_t)d * zws) : 0u;
             zp[u] += 5 * zws;                                   // next word to fetch
         }
         double acc[PPT][4], lnsc[PPT];
@@ -119,14 +126,12 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
         auto take = [&](int f, unsigned int (&off)[PPT]) {
             const int adv = (f >> 2) & 3;
             if (adv) {
-                const int k = (f >> 4) & 3;
+                // shift the queue (three register moves per pattern every fourth tip: cheaper than indexing it, which made
+                // the compiler clone the op bodies per queue position) and fetch the word four ahead
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
-                    const unsigned int* src = zp[u];
-                    if (k == 0)      { cw[u] = r[u][0]; if (adv == 1) r[u][0] = __ldg(src); }
-                    else if (k == 1) { cw[u] = r[u][1]; if (adv == 1) r[u][1] = __ldg(src); }
-                    else if (k == 2) { cw[u] = r[u][2]; if (adv == 1) r[u][2] = __ldg(src); }
-                    else             { cw[u] = r[u][3]; if (adv == 1) r[u][3] = __ldg(src); }
+                    cw[u] = r[u][0]; r[u][0] = r[u][1]; r[u][1] = r[u][2]; r[u][2] = r[u][3];
+                    if (adv == 1) r[u][3] = __ldg(zp[u]);
                     zp[u] += zws;
                 }
             }
@@ -138,9 +143,20 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             const double2 a = ldP(node_off, off), b = ldP(node_off, off + 16u);
             c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
         };
-        auto load16 = [&](unsigned int node_off, double (&Pr)[16]) {
+        // the 4x4 matrix of internal branch `node` (warp-uniform): uniform constant loads when PCONST, else 8 broadcast loads
+        auto load16 = [&](int node, int op, double (&Pr)[16]) {
+            if (PCONST) {
+                // the node index is re-read from the constant-memory op word with the (uniform) op counter, so that the
+                // compiler can see the address is warp-uniform and use the uniform datapath (LDCU -> UR operands of DFMA)
+                const int ci = (c_prog[2 * op + 1] & 0xffff) * 16 + p.cp_base + (int)blockIdx.y * p.cp_class_stride;
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) { const double2 t = ldP(node_off, 8u * e); Pr[e] = t.x; Pr[e + 1] = t.y; }
+                for (int e = 0; e < 16; e++) Pr[e] = c_P4[ci + e];
+            }
+            else {
+                const unsigned int node_off = (unsigned int)node * pstride_b;
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) { const double2 t = ldP(node_off, 8u * e); Pr[e] = t.x; Pr[e + 1] = t.y; }
+            }
         };
         auto matvec = [&](const double (&Pr)[16], const double (&v)[4], double (&t)[4]) {
 #pragma unroll
@@ -158,11 +174,13 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
 
         int nw0, nw1;
         op_words(0, nw0, nw1);
+#pragma unroll 1
         for (int op = 0; op < nops; op++) {
             const int w0 = nw0, w1 = nw1;
             op_words(op + 1 < nops ? op + 1 : op, nw0, nw1);            // the next op's words are in flight during this op
             const int opc = w0 & 15;
-            const unsigned int a_off = (unsigned int)(w1 & 0xffff) * pstride_b, b_off = ((unsigned int)w1 >> 16) * pstride_b;
+            const int a_node = w1 & 0xffff;
+            const unsigned int a_off = (unsigned int)a_node * pstride_b, b_off = ((unsigned int)w1 >> 16) * pstride_b;
             const unsigned int sl = slot0 + (((unsigned int)w0 >> M4_SLOT_SHIFT) & 255u) * SLOT_BYTES;
             switch (opc) {
             case M4_CHERRY: {
@@ -181,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             case M4_MV_TIP: {
                 // internal child still in registers (src/baseml.c:1559-1566), then a tip child
                 double Pr[16];
-                load16(a_off, Pr);
+                load16(a_node, op, Pr);
                 unsigned int ob[PPT];
                 take(w0 >> M4_TIPF0_SHIFT, ob);
 #pragma unroll
@@ -196,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             }
             case M4_MV_PUSH: {
                 double Pr[16];
-                load16(a_off, Pr);
+                load16(a_node, op, Pr);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double t[4];
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             }
             case M4_MV_POP: {
                 double Pr[16];
-                load16(a_off, Pr);
+                load16(a_node, op, Pr);
 #pragma unroll
                 for (int u = 0; u < PPT; u++) {
                     double t[4];
