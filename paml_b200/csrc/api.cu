@@ -408,6 +408,9 @@ static int pick_launch(int NT, int mt_small, PruneLaunch* L)
 {
     const char* renv = getenv("PB200_REGS255");      // tuning: the 8-pattern codon kernel compiled for <= 8 warps (255 registers)
     if (NT == 8 && mt_small && renv && atoi(renv)) { *L = make_launch<8, 16, 1, 8>(); return 0; }
+    const char* wenv = getenv("PB200_MAXW");         // tuning: register budget for 20 / 24 resident warps per SM (102 / 85 registers)
+    if (NT == 8 && mt_small && wenv && atoi(wenv) == 20) { *L = make_launch<8, 16, 1, 20>(); return 0; }
+    if (NT == 8 && mt_small && wenv && atoi(wenv) == 24) { *L = make_launch<8, 16, 1, 24>(); return 0; }
     if (NT == 8) *L = mt_small ? make_launch<8, 16, 1, 16>() : make_launch<8, 16, 2, 8>();
     else if (NT == 3) *L = mt_small ? make_launch<3, 5, 1, 16>() : make_launch<3, 5, 2, 16>();
     else if (NT == 1) *L = mt_small ? make_launch<1, 1, 1, 16>() : make_launch<1, 1, 4, 16>();
@@ -759,7 +762,13 @@ static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const doub
 static int launch_prune4v2(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
 {
     const char* e = getenv("PB200_NUC_PPT");
-    const int v = e ? atoi(e) : 2;
+    // Default shape (measured on the cfg-5 shape, profiles/r2_sweeps.txt): with the internal branches' matrices in c_P4, 4 patterns
+    // per thread amortise the 16 uniform loads of an op best (0.51 of the DFMA peak against 0.45 for the shared-memory variant);
+    // trees too large for c_P4 (more than 320 internal nodes) or for the constant-memory program keep the 2-pattern shape
+    const char* pcenv = getenv("PB200_NUC_PCONST");
+    const bool pconst_ok = c->plan4.ops.size() <= PB200_CONST_PROG_INTS && !getenv("PB200_NO_CONST_PROG") && !(pcenv && atoi(pcenv) == 0) &&
+                           (c->nnode - c->ns) * 16 <= PB200_CONST_P4_DOUBLES;
+    const int v = e ? atoi(e) : (pconst_ok ? 4 : 2);
     if (v == 1) return launch_prune4v2_t<1, 256, 3>(c, nclass, semantics, d_pi);
     if (v == 4) return launch_prune4v2_t<4, 128, 2>(c, nclass, semantics, d_pi);
     if (v == 41) return launch_prune4v2_t<4, 256, 1>(c, nclass, semantics, d_pi);
@@ -767,6 +776,13 @@ static int launch_prune4v2(pb200_ctx* c, int nclass, int semantics, const double
     if (v == 3) return launch_prune4v2_t<3, 128, 3>(c, nclass, semantics, d_pi);
     if (v == 23) return launch_prune4v2_t<2, 384, 2>(c, nclass, semantics, d_pi);
     if (v == 13) return launch_prune4v2_t<1, 512, 2>(c, nclass, semantics, d_pi);
+    if (v == 43) return launch_prune4v2_t<4, 128, 3>(c, nclass, semantics, d_pi);
+    if (v == 44) return launch_prune4v2_t<4, 64, 4>(c, nclass, semantics, d_pi);
+    if (v == 46) return launch_prune4v2_t<4, 64, 6>(c, nclass, semantics, d_pi);
+    if (v == 6) return launch_prune4v2_t<6, 128, 2>(c, nclass, semantics, d_pi);
+    if (v == 8) return launch_prune4v2_t<8, 64, 2>(c, nclass, semantics, d_pi);
+    if (v == 84) return launch_prune4v2_t<8, 64, 4>(c, nclass, semantics, d_pi);
+    if (v == 32) return launch_prune4v2_t<3, 256, 2>(c, nclass, semantics, d_pi);
     return launch_prune4v2_t<2, 256, 2>(c, nclass, semantics, d_pi);
 }
 

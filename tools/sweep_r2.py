@@ -61,6 +61,32 @@ if what in ("nuc", "all"):
          ("PCONST ppt4 128x2", dict(PB200_NUC_PPT="4")),
          ("PCONST ppt4 256x1", dict(PB200_NUC_PPT="41"))]
     sweep("cfg5", p, V, dfma)
+if what == "nuc2":
+    p = simulate.nuc_gtr_gamma_problem()
+    V = [("PCONST ppt4 128x2", dict(PB200_NUC_PPT="4")),
+         ("v2 ppt4 128x2 (P in smem)", dict(PB200_NUC_PPT="4", PB200_NUC_PCONST="0")),
+         ("PCONST ppt4 128x3", dict(PB200_NUC_PPT="43")),
+         ("PCONST ppt4 64x4", dict(PB200_NUC_PPT="44")),
+         ("PCONST ppt4 64x6", dict(PB200_NUC_PPT="46")),
+         ("PCONST ppt6 128x2", dict(PB200_NUC_PPT="6")),
+         ("PCONST ppt8 64x2", dict(PB200_NUC_PPT="8")),
+         ("PCONST ppt8 64x4", dict(PB200_NUC_PPT="84")),
+         ("PCONST ppt3 256x2", dict(PB200_NUC_PPT="32")),
+         ("PCONST ppt4 128x2, 1 class/launch", dict(PB200_NUC_PPT="4", PB200_NUC_CLS_PER_LAUNCH="1")),
+         ("v2 ppt8 64x4 (P in smem)", dict(PB200_NUC_PPT="84", PB200_NUC_PCONST="0")),
+         ("v2 ppt6 128x2 (P in smem)", dict(PB200_NUC_PPT="6", PB200_NUC_PCONST="0"))]
+    sweep("cfg5", p, V, dfma)
+if what == "codon2":
+    p = simulate.codon_m0_problem(npatt=100_000, seed=13147)
+    V = [("default", dict()), ("regs for 20 warps/SM", dict(PB200_MAXW="20")), ("regs for 24 warps/SM", dict(PB200_MAXW="24"))]
+    sweep("cfg2", p, V, dmma)
+    q = simulate.Problem(**{k: getattr(p, k) for k in p.__dataclass_fields__})
+    q.z = np.zeros_like(p.z)
+    sweep("cfg2 z=0", q, V[:1], dmma)             # every tip gather hits the same row: tip phases without their L2 traffic
+    q.z = (np.arange(p.npatt)[None, :] // 8 % 61 + np.zeros((p.ns, 1), int)).astype(np.uint8)
+    sweep("cfg2 z=tile", q, V[:1], dmma)          # the 8 patterns of a warp share their codes: one row per gather instruction
+    p = simulate.codon_sites_problem(npatt=50_000, seed=13149, freqs=(0.4, 0.3, 0.2, 0.1), omegas=(0.05, 0.3, 1.0, 2.5))
+    sweep("cfg3_K4", p, V, dmma)
 if what in ("codon", "all"):
     p = simulate.codon_m0_problem(npatt=100_000, seed=13147)
     V = [("default", dict()),
