@@ -18,6 +18,7 @@
 #include "prune4v2.cuh"
 #include "eigen.cuh"
 #include "cond.cuh"
+#include "cond_dmma.cuh"
 #include "plan.h"
 
 using namespace pb200;
@@ -130,6 +131,7 @@ struct pb200_ctx {
     size_t h_cstage_cap = 0;
     void* h_cbr = nullptr;      // pinned: per-call inputs of pb200_branch_lnl + its 3 results
     int cond_nclass = 0, cond_nscale = 0;
+    bool cond_dmma = false;     // the resident-vector kernels run on the DMMA path (n > 4; PB200_COND_DMMA=0 keeps the FP64-vector kernels)
     struct { int kind, nr, nset; long long set_stride; size_t off_sets; bool ok; } csets = {0, 0, 0, 0, 0, false};
     DevBuf d_eig;               // pb200_eigen_qrev: Q | pi | sets | info
     void* h_eig = nullptr;      // its pinned mirror
@@ -788,9 +790,10 @@ static int launch_prune4v2(pb200_ctx* c, int nclass, int semantics, const double
 
 static int launch_pt(pb200_ctx* c, int n, int kind, int nr, long long set_stride, const double* d_sets, int nmat,
                      const int* d_mat_set, const double* d_mat_t, double* d_out, long long pstride, int mode, int nnode, int ns,
-                     int NT, int KS, int ncodes)
+                     int NT, int KS, int ncodes, int logical = 0)
 {
     PtParams p;
+    p.logical = logical;
     p.n = n; p.NT = NT; p.KS = KS; p.ld = 4 * KS; p.ncodes = ncodes; p.ns = ns; p.nnode = nnode;
     p.kind = kind; p.nr = nr; p.set_stride = set_stride; p.sets = d_sets; p.mat_set = d_mat_set; p.mat_t = d_mat_t;
     p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
@@ -1259,7 +1262,12 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
         CUDA_TRY(cudaMallocHost(&c->h_cstage, total + total / 4));
         c->h_cstage_cap = total + total / 4;
     }
-    if (c->d_cstage.ensure(total) || c->d_cP.ensure((size_t)nmat * n * n * 8)) return 1;
+    {
+        const char* denv = getenv("PB200_COND_DMMA");
+        c->cond_dmma = (n > 4) && !(denv && atoi(denv) == 0);
+    }
+    const long long cpstride = c->cond_dmma ? c->pstride : (long long)n * n;
+    if (c->d_cstage.ensure(total) || c->d_cP.ensure((size_t)nmat * cpstride * 8)) return 1;
     char* hs = (char*)c->h_cstage;
     char* ds = (char*)c->d_cstage.p;
     if (set_stride > 0) memcpy(hs + off_sets, set_data, (size_t)nset * set_stride * 8);
@@ -1269,7 +1277,36 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
     CUDA_TRY(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, c->stream));
     c->csets.kind = set_kind; c->csets.nr = nr; c->csets.nset = nset; c->csets.set_stride = set_stride; c->csets.off_sets = off_sets;
     c->csets.ok = true;
-    if (nupd) {
+    static bool attr_set[64] = {false};
+    if (c->device < 64 && !attr_set[c->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(cond_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 5 * COND_TP * 65) * 8));
+        CUDA_TRY(cudaFuncSetAttribute(branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (3 * 64 * 64 + 2 * COND_TP * 65 + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * 8));
+        attr_set[c->device] = true;
+    }
+    if (nupd && c->cond_dmma) {
+        // tensor path: P(t) of the branches this call reads, tip rows / B fragments in logical state order
+        if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
+                      (const double*)(ds + off_t), (double*)c->d_cP.p, c->pstride, PT_MODE_AUTO, nnode, ns, c->NT, c->KS, c->ncodes, 1))
+            return 1;
+        const long long ntile = (c->npatt + 7) / 8;
+        for (int u = 0; u < nupd; u++) {
+            CondDmmaParams p;
+            p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.nson = upd_nson[u]; p.node = upd_node[u];
+            p.scale_k = scale_k[upd_node[u]]; p.nscale = nscale; p.npatt = c->npatt; p.zstride = c->zstride; p.pstride = c->pstride;
+            p.ntiles = ntile;
+            p.sons = (const int*)(ds + off_sons) + (size_t)u * maxsons;
+            p.P = (const double*)c->d_cP.p; p.z = (const unsigned char*)c->d_z.p;
+            p.cond = (double*)c->d_cond.p; p.scaleF = (double*)c->d_cscale.p;
+            const long long want = (ntile * nclass + 3) / 4;
+            const int grid = (int)std::min<long long>(want, (long long)c->nsm * 4);
+            if (c->NT == 8) cond_node_dmma_kernel<8, 16><<<grid, 128, 0, c->stream>>>(p);
+            else            cond_node_dmma_kernel<3, 5><<<grid, 128, 0, c->stream>>>(p);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    else if (nupd) {
         if (launch_pt(c, n, set_kind, nr, set_stride, (const double*)(ds + off_sets), nmat, (const int*)(ds + off_set),
                       (const double*)(ds + off_t), (double*)c->d_cP.p, (long long)n * n, PT_MODE_PLAIN_T, nnode, ns, c->NT, c->KS, c->ncodes))
             return 1;
@@ -1277,13 +1314,6 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
         const long long ntile = (c->npatt + COND_TP - 1) / COND_TP;
         int tiles = (int)std::min<long long>(4, std::max<long long>(1, ntile * nclass / (2LL * c->nsm)));
         const size_t smem = ((size_t)n * COND_LDP + (size_t)(1 + tiles) * COND_TP * (n | 1)) * sizeof(double);
-        static bool attr_set[64] = {false};
-        if (c->device < 64 && !attr_set[c->device]) {
-            CUDA_TRY(cudaFuncSetAttribute(cond_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 64 + 5 * COND_TP * 65) * 8));
-            CUDA_TRY(cudaFuncSetAttribute(branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (3 * 64 * 64 + 2 * COND_TP * 65 + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * 8));
-            attr_set[c->device] = true;
-        }
         for (int u = 0; u < nupd; u++) {
             CondNodeParams p;
             p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.nson = upd_nson[u]; p.node = upd_node[u];
@@ -1320,10 +1350,19 @@ extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, i
     size_t off_s = align16(off_pi + (size_t)n * 8), off_r = align16(off_s + (size_t)nclass * 4), total = off_r + 32;
     if (!c->h_cbr) CUDA_TRY(cudaMallocHost(&c->h_cbr, 1 << 16));
     if (total > (1 << 16)) return fail("pb200_branch_lnl: too many classes");
-    const long long ntile = (c->npatt + COND_TP - 1) / COND_TP;
+    const bool dmma = c->cond_dmma;
+    const int NTP = (c->NT + 1) / 2;
+    const long long p3stride = dmma ? (long long)c->KS * NTP * 64 : (long long)n * n;
+    long long ntile = dmma ? (c->npatt + 7) / 8 : (c->npatt + COND_TP - 1) / COND_TP;
     const int tiles = (int)std::min<long long>(COND_TMAX, std::max<long long>(1, ntile / (2LL * c->nsm)));
-    const int nblk = (int)((ntile + tiles - 1) / tiles);
-    if (c->d_cbr.ensure(total) || c->d_cP3.ensure((size_t)nclass * 3 * n * n * 8) || c->d_cpart.ensure((size_t)nblk * 3 * 8) || c->d_cres.ensure(32))
+    int nblk;                                  // partial triples the final sum adds: blocks (vector kernels) or warps (tensor path)
+    int grid_dmma = 0;
+    if (dmma) {
+        grid_dmma = (int)std::min<long long>((ntile + 3) / 4, (long long)c->nsm * 3);
+        nblk = grid_dmma * 4;
+    }
+    else nblk = (int)((ntile + tiles - 1) / tiles);
+    if (c->d_cbr.ensure(total) || c->d_cP3.ensure((size_t)nclass * 3 * p3stride * 8) || c->d_cpart.ensure((size_t)nblk * 3 * 8) || c->d_cres.ensure(32))
         return 1;
     char* hs = (char*)c->h_cbr;
     char* ds = (char*)c->d_cbr.p;
@@ -1332,24 +1371,47 @@ extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, i
     memcpy(hs + off_pi, pi, (size_t)n * 8);
     memcpy(hs + off_s, set_of_class, (size_t)nclass * 4);
     CUDA_TRY(cudaMemcpyAsync(ds, hs, off_r, cudaMemcpyHostToDevice, c->stream));
-    Pt3Params q;
-    q.n = n; q.kind = c->csets.kind; q.nr = c->csets.nr; q.nclass = nclass; q.set_stride = c->csets.set_stride;
-    q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + off_s);
-    q.mult = (const double*)(ds + off_m); q.t = t; q.out = (double*)c->d_cP3.p;
-    pt3_kernel<<<nclass, 256, 0, c->stream>>>(q);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    BranchParams p;
-    p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.a = a; p.b = b; p.nscale = c->cond_nscale;
-    p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride; p.tiles = tiles;
-    p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
-    p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
-    p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
-    p.partial = (double*)c->d_cpart.p;
-    const size_t smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * sizeof(double);
-    branch_kernel<<<nblk, COND_THREADS, smem, c->stream>>>(p);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
+    if (dmma) {
+        Pt3FragParams q;
+        q.n = n; q.kind = c->csets.kind; q.nr = c->csets.nr; q.nclass = nclass; q.NT = c->NT; q.KS = c->KS;
+        q.set_stride = c->csets.set_stride; q.p3stride = p3stride;
+        q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + off_s);
+        q.mult = (const double*)(ds + off_m); q.t_dev = nullptr; q.t = t; q.out = (double*)c->d_cP3.p;
+        pt3_frag_kernel<<<nclass, 256, 0, c->stream>>>(q);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        BranchDmmaParams p;
+        p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.a = a; p.b = b; p.nscale = c->cond_nscale;
+        p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride; p.ntiles = ntile; p.p3stride = p3stride;
+        p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
+        p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
+        p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
+        p.partial = (double*)c->d_cpart.p;
+        if (c->NT == 8) branch_dmma_kernel<8, 16><<<grid_dmma, 128, 0, c->stream>>>(p);
+        else            branch_dmma_kernel<3, 5><<<grid_dmma, 128, 0, c->stream>>>(p);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    else {
+        Pt3Params q;
+        q.n = n; q.kind = c->csets.kind; q.nr = c->csets.nr; q.nclass = nclass; q.set_stride = c->csets.set_stride;
+        q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + off_s);
+        q.mult = (const double*)(ds + off_m); q.t = t; q.out = (double*)c->d_cP3.p;
+        pt3_kernel<<<nclass, 256, 0, c->stream>>>(q);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        BranchParams p;
+        p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.a = a; p.b = b; p.nscale = c->cond_nscale;
+        p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride; p.tiles = tiles;
+        p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
+        p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
+        p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
+        p.partial = (double*)c->d_cpart.p;
+        const size_t smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * sizeof(double);
+        branch_kernel<<<nblk, COND_THREADS, smem, c->stream>>>(p);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     cond_sum_kernel<<<1, 256, 0, c->stream>>>((const double*)c->d_cpart.p, nblk, (double*)c->d_cres.p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -50,6 +50,7 @@ struct PtParams {
     double* out;        // [nmat][pstride]
     long long pstride;
     int mode;           // PT_MODE_*
+    int logical;        // 1: tip rows / B fragments in LOGICAL state order (cond_dmma.cuh) instead of the physical order of prune_kernel
 };
 
 // grid = (matrices, row blocks): CTA (m, rb) computes rows [16rb, 16rb+16) of matrix m with 256 threads
@@ -227,11 +228,11 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
                 }
             }
             // physical position of logical state j (inverse of phys_to_logical)
-            int ph = (j & ~7) | ((j & 3) << 1) | ((j >> 2) & 1);
+            int ph = p.logical ? j : ((j & ~7) | ((j & 3) << 1) | ((j >> 2) & 1));
             out[(size_t)code * NP + ph] = v;
         }
         if (rb == 0)                                         // padded parent states beyond ld (none when NP == ld)
-            for (int e = tid; e < p.ncodes * NP; e += 256) { int ph = e % NP; if (phys_to_logical(ph) >= ld) out[e] = 0.0; }
+            for (int e = tid; e < p.ncodes * NP; e += 256) { int ph = e % NP; if ((p.logical ? ph : phys_to_logical(ph)) >= ld) out[e] = 0.0; }
     }
     else {
         // DMMA B-fragment order, two n-tiles per 16-byte element so that one 128-bit load feeds two DMMAs:
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(256) pt_kernel(const PtParams p)
         for (int e0 = tid; e0 < total; e0 += 256) {
             int e = e0 & 1, lane = (e0 >> 1) & 31, f = e0 >> 6, pr = f % NTP, ks = f / NTP;
             int nt = 2 * pr + e;
-            int j = phys_to_logical(8 * nt + (lane >> 2)), k = 4 * ks + (lane & 3);
+            int j = p.logical ? (8 * nt + (lane >> 2)) : phys_to_logical(8 * nt + (lane >> 2)), k = 4 * ks + (lane & 3);
             bool mine = (j >= i0 && j < i0 + 16);
             bool pad = (nt >= p.NT || j >= ld);               // entries no row block owns: zero them from block 0
             if (mine) out[e0] = (nt < p.NT && j < n && k < n) ? Prow[(j - i0) * ld + k] : 0.0;

@@ -52,6 +52,7 @@ class Problem:
     nscale: int = 0
     branch_len: np.ndarray = None  # float64 [nnode]: the tree's own branch lengths (synthetic problems; branch_t = these x class rate)
     model_name: str = None
+    branch_rec: dict = None        # branch fixtures: a, b, siteclass, t and the reference's lfuntdd outputs l, dl, ddl
 
     @property
     def ninternal(self):
@@ -109,5 +110,10 @@ def load_fixture(path):
     Ps = take(np.float64, ndump * n * n).reshape(ndump, n, n)
     p.ref_P = [(int(cls[i]), int(node[i]), Ps[i]) for i in range(ndump)]
     p.x = take(np.float64, max(np_, 0))
+    if buf[off:off + 8] == b"BRLN0001":        # branch fixture (oracle/ref_hook.inc, PBX_BRANCH_DUMP)
+        off += 8
+        a, b, sc, _ = [int(v) for v in take(np.int32, 4)]
+        t, l, dl, ddl, blen = [float(v) for v in take(np.float64, 5)]
+        p.branch_rec = dict(a=a, b=b, siteclass=sc, t=t, l=l, dl=dl, ddl=ddl, branch_len=blen)
     assert off == len(buf), "fixture has trailing bytes"
     return p

@@ -94,6 +94,43 @@ CASES = [
 ]
 
 
+# Branch fixtures (tests/golden/branch/): `method = 1` runs stopped at the k-th lfuntdd / lfuntdd_SiteClass call with an internal
+# b; the fixture holds the tree as minbranches had rerooted it and the reference's -lnL(t), d/dt, d2/dt2 of that branch.
+BRANCH_CASES = [
+    dict(name="lysozyme_m0_branch", prog="codeml", ctl="lysozyme/lysozymeSmall.ctl", files=["lysozyme/lysozymeSmall.nuc", "lysozyme/lysozymeSmall.trees"],
+         ov=dict(seqfile="lysozymeSmall.nuc", treefile="lysozymeSmall.trees", model=0, NSsites=0, CodonFreq=2, getSE=0, RateAncestor=0, noisy=0, method=1), call=4),
+    dict(name="lysozyme_m2a_branch", prog="codeml", ctl="lysozyme/lysozymeSmall.ctl", files=["lysozyme/lysozymeSmall.nuc", "lysozyme/lysozymeSmall.trees"],
+         ov=dict(seqfile="lysozymeSmall.nuc", treefile="lysozymeSmall.trees", model=0, NSsites=2, CodonFreq=2, getSE=0, RateAncestor=0, noisy=0, method=1), call=9),
+    dict(name="brown_hky_g4_branch", prog="baseml", ctl="baseml.ctl", files=["brown.nuc", "brown.trees"],
+         ov=dict(seqfile="brown.nuc", treefile="brown.trees", model=4, fix_alpha=0, alpha=0.5, ncatG=4, getSE=0, RateAncestor=0, method=1, noisy=0), call=2),
+    dict(name="stewart_wag_g4_branch", prog="codeml", ctl="aaml.ctl", files=["stewart.aa", "stewart.trees"],
+         ov=dict(seqfile="stewart.aa", treefile="stewart.trees", seqtype=2, model=2, aaRatefile=os.path.join(REF, "dat", "wag.dat"),
+                 fix_alpha=0, alpha=0.5, ncatG=4, getSE=0, RateAncestor=0, noisy=0, cleandata=1, method=1), call=3),
+    dict(name="mhc_m0_branch", prog="codeml", ctl="MHC.Swanson2002MBE/codeml.ctl", files=["MHC.Swanson2002MBE/bigmhc.phy", "MHC.Swanson2002MBE/bigmhc.trees"],
+         ov=dict(seqfile="bigmhc.phy", treefile="bigmhc.trees", NSsites=0, method=1, fix_blength=1, getSE=0, RateAncestor=0, noisy=0), call=150),
+]
+
+
+def run_branch_case(c, workroot):
+    w = os.path.join(workroot, c["name"])
+    os.makedirs(w, exist_ok=True)
+    for f in c["files"]:
+        shutil.copy(os.path.join(EX, f), w)
+    ov = dict(c["ov"]); ov["outfile"] = "out.txt"
+    write_ctl(os.path.join(w, "run.ctl"), os.path.join(EX, c["ctl"]), ov)
+    fx = os.path.join(w, c["name"] + ".pbfx")
+    env = dict(os.environ, PBX_BRANCH_DUMP=fx, PBX_BRANCH_CALL=str(c["call"]))
+    r = subprocess.run([HOOK[c["prog"]], "run.ctl"], cwd=w, env=env, stdin=subprocess.DEVNULL,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    m = re.search(r"pbx: branch record (.*)", r.stdout)
+    if r.returncode != 0 or not m:
+        print(r.stdout[-3000:])
+        raise SystemExit("branch case %s failed (rc=%d)" % (c["name"], r.returncode))
+    os.makedirs(os.path.join(OUT, "branch"), exist_ok=True)
+    shutil.copy(fx, os.path.join(OUT, "branch", c["name"] + ".pbfx"))
+    print("%-24s %s  %d bytes" % (c["name"], m.group(1), os.path.getsize(fx)))
+
+
 def add_ambiguity(path_in, path_out, kind):
     """Deterministically sprinkle ambiguity characters into a PHYLIP file whose names sit on their own lines."""
     lines = open(path_in).read().splitlines()
@@ -158,3 +195,7 @@ if __name__ == "__main__":
         if only and c["name"] not in only:
             continue
         run_case(c, workroot)
+    for c in BRANCH_CASES:
+        if only and c["name"] not in only:
+            continue
+        run_branch_case(c, workroot)

@@ -182,3 +182,37 @@ def test_set_tree_invalidates_resident_vectors_and_begin_checks_pending():
     with pytest.raises(PB200Error):
         t.eval_problem(p)
     t.close()
+
+
+import glob as _glob
+import os as _os
+BRANCH_FIXTURES = sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "branch", "*.pbfx")))
+
+
+@pytest.mark.parametrize("path", BRANCH_FIXTURES, ids=[_os.path.basename(f)[:-5] for f in BRANCH_FIXTURES])
+@pytest.mark.parametrize("dmma", ["1", "0"])
+def test_branch_derivatives_against_reference_lfuntdd(path, dmma, monkeypatch):
+    """pb200_branch_lnl against the REFERENCE's own lfuntdd / lfuntdd_SiteClass (src/treesub.c:8204-8300, 8405-8543): fixtures
+    dumped by oracle/ref_hook.inc from `method = 1` runs of the unmodified reference, stopped inside minbranches -- the tree as
+    rerooted at that moment (root = b), the parameters and branch lengths of that moment, and the reference's -lnL(t), d/dt and
+    d2/dt2 for the branch b -> a.  Both kernel families are checked: the tensor path (n > 4) and the FP64-vector kernels."""
+    monkeypatch.setenv("PB200_COND_DMMA", dmma)
+    p = load_fixture(path)
+    r = p.branch_rec
+    a, b = r["a"], r["b"]
+    assert b == p.root and a >= p.ns
+    if dmma == "1" and p.n <= 4:
+        pytest.skip("4-state alphabets use the vector kernels only")
+    t_ = TreeLikelihood(0)
+    t_.set_problem(p)
+    sons = _sons(p)
+    own = dict(sons); own[b] = [c for c in sons[b] if c != a]          # b keeps the vector of its side only (src/treesub.c:8080-8083)
+    upd = _postorder(p, a, sons) + _postorder(p, b, own)
+    flags = p.scale_flags if p.nscale else None
+    t_.cond_update(p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, upd, flags)
+    mult = p.branch_t[:, a] / r["branch_len"]
+    out = t_.branch_lnl(p.freqK, a, b, r["t"], mult, p.branch_set[:, a], p.pi[:p.n], 1 if r["siteclass"] else 0, True)
+    t_.close()
+    assert abs(out[0] - r["l"]) <= 1e-10 * abs(r["l"]), (out[0], r["l"])
+    assert abs(out[1] - r["dl"]) <= 1e-8 * max(1.0, abs(r["dl"])) + 1e-10 * abs(r["ddl"]), (out[1], r["dl"])
+    assert abs(out[2] - r["ddl"]) <= 1e-8 * abs(r["ddl"]), (out[2], r["ddl"])
