@@ -213,19 +213,12 @@ def test_codeml_m2a_neb_beb_fixed_point(tmp_path):
 # ---- method = 1: minbranches on conditional vectors resident in HBM ----
 
 def _close_method1(res, prog, write0, outfile, tmp_path, rel=2e-6):
-    """method = 1 alternates two optimisers and its trajectory is sensitive to the last bits of the likelihood: on some data
-    the reference itself stops at a poor point (e.g. HKY+G4 below: -4760.79 with alpha at its bound, where method = 0 finds
-    -4571.69).  The drop-in must reproduce the reference's method = 1 result or, failing that, the optimum the reference finds
-    with method = 0 -- never something else."""
+    """method = 1 alternates two optimisers (ming2 on the substitution parameters, Newton steps on one branch at a time).  Both
+    programs start every fit from the same values (PB200_TEST_SEED / oracle/fixed_seed.c), every evaluation agrees with the
+    reference to ~1e-13, so the drop-in must follow the reference's own method = 1 trajectory and end where it ends -- also when
+    that end point is a poor one (e.g. HKY+G4 from some starts: alpha at its bound).  No second chance against method = 0."""
     g, r = res["gpu"][0], res["ref"][0]
-    if abs(g - r) <= rel * abs(r):
-        return
-    d = tmp_path / "ref_method0"
-    d.mkdir()
-    write0(str(d))
-    _run(os.path.join(REF, prog), str(d))
-    r0 = _lnl(str(d / outfile))
-    assert abs(g - r0) <= rel * abs(r0), dict(gpu_method1=g, ref_method1=r, ref_method0=r0)
+    assert abs(g - r) <= rel * abs(r), dict(gpu_method1=g, ref_method1=r)
 
 
 def _fixed_start(path, ntime, tail):
@@ -356,8 +349,6 @@ def test_method1_ancestral_reconstruction_with_site_classes(tmp_path):
         _fixed_start(d + "/in.baseml", 2 * p.ns - 3, [2.0, 0.5])
     res = _both(tmp_path, "baseml", write, "mlb")
     _close_method1(res, "baseml", lambda d: write(d, 0), "mlb", tmp_path)
-    if abs(res["gpu"][0] - res["ref"][0]) > 2e-6 * abs(res["ref"][0]):
-        pytest.skip("the two method = 1 trajectories parted (see _close_method1): no common point to compare reconstructions at")
     g, r = _numbers(res["gpu"][1] + "/rst"), _numbers(res["ref"][1] + "/rst")
     assert len(g) == len(r) and len(r) > 500, (len(g), len(r))
     # both programs start their iteration from randomly perturbed initial values (src/baseml.c:1253-1263): the two fits agree to
