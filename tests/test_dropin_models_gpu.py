@@ -313,6 +313,53 @@ def test_method1_codeml_free_ratio(tmp_path):
     _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "codeml_b200"))
 
 
+@pytest.mark.parametrize("mgene,malpha,gamma", [(0, 0, False), (2, 0, False), (3, 0, True), (4, 1, True)])
+def test_method1_baseml_genes(tmp_path, mgene, malpha, gamma):
+    """method = 1 with several genes / partitions (round 2; round 1 ran these on the reference's CPU routines): every gene's
+    conditional vectors live in that gene's context and are updated with that gene's parameters (SetPGene: kappa, pi, rgene,
+    alpha), lfuntdd / lfuntdd_SiteClass sum over the genes (src/treesub.c:8239-8241, 8472-8476)."""
+    p = simulate.nuc_gtr_gamma_problem(ns=6, npatt=240, seed=37, K=4)
+    n = int(p.npatt)
+
+    def write(d, method=1):
+        paml_io.write_pattern_files(p, d + "/s", genes=[n - n // 3, n // 3])
+        _baseml_ctl(d + "/run.ctl", Mgene=mgene, Malpha=malpha, model=4, fix_alpha=(0 if gamma else 1), alpha=("0.5" if gamma else "0"),
+                    ncatG=(4 if gamma else 1))
+        txt = open(d + "/run.ctl").read().replace("method = 0", "method = %d" % method)
+        open(d + "/run.ctl", "w").write(txt)
+    res = _both(tmp_path, "baseml", write, "mlb")
+    _close_method1(res, "baseml", lambda d: write(d, 0), "mlb", tmp_path)
+    _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "baseml_b200"))
+
+
+def test_method1_codeml_genes(tmp_path):
+    """Codon partitions with their own kappa, omega and codon frequencies (Mgene = 4) under method = 1."""
+    p = simulate.codon_m0_problem(ns=6, npatt=180, seed=39)
+    n = int(p.npatt)
+
+    def write(d, method=1):
+        paml_io.write_pattern_files(p, d + "/s", genes=[n // 2, n - n // 2])
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", kappa=2.0, omega=0.4,
+                                 extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, Mgene=4, method=method))
+    res = _both(tmp_path, "codeml", write, "mlc")
+    _close_method1(res, "codeml", lambda d: write(d, 0), "mlc", tmp_path, rel=5e-6)
+    _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "codeml_b200"))
+
+
+def test_method1_aaml_poisson(tmp_path):
+    """aaml Poisson under method = 1: the evaluation uses the closed form (PMatJC69like), minbranches the spectral form eigenQaa
+    left in Root / U / V once for all -- on the GPU since round 2."""
+    p = simulate.aa_gamma_problem(ns=7, npatt=150, seed=51, K=1)
+
+    def write(d, method=1):
+        paml_io.write_pattern_files(p, d + "/s")
+        paml_io.write_codeml_ctl(d + "/run.ctl", "s.phy", "s.tre", seqtype=2,
+                                 extra=dict(model=0, fix_alpha=1, alpha=0, ncatG=1, fix_blength=1, method=method))
+    res = _both(tmp_path, "codeml", write, "mlc")
+    _close_method1(res, "codeml", lambda d: write(d, 0), "mlc", tmp_path)
+    _verbose_says_gpu(res["gpu"][1], os.path.join(BIN, "codeml_b200"))
+
+
 def test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path):
     """Where minbranches is NOT mapped to the GPU (PB200_MINB=0 forces that here) the reference's CPU routines run on
     nodes[].conP, which the GPU likelihood never fills: the shim refreshes them with the reference's own CPU evaluation

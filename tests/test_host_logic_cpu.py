@@ -112,6 +112,19 @@ def test_method1_free_ratio(shim, tmp_path):
     T.test_method1_codeml_free_ratio(tmp_path)
 
 
+@pytest.mark.parametrize("mgene,malpha,gamma", [(0, 0, False), (2, 0, False), (3, 0, True), (4, 1, True)])
+def test_method1_baseml_genes(shim, tmp_path, mgene, malpha, gamma):
+    T.test_method1_baseml_genes(tmp_path, mgene, malpha, gamma)
+
+
+def test_method1_codeml_genes(shim, tmp_path):
+    T.test_method1_codeml_genes(tmp_path)
+
+
+def test_method1_aaml_poisson(shim, tmp_path):
+    T.test_method1_aaml_poisson(tmp_path)
+
+
 def test_method1_cpu_minbranches_paths(shim, tmp_path):
     T.test_method1_cpu_minbranches_paths_get_fresh_host_vectors(tmp_path)
 
