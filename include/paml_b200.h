@@ -113,6 +113,16 @@ int pb200_pmat(pb200_ctx *ctx, int n, int set_kind, int nr, int nset, long long 
 int pb200_eigen_qrev(pb200_ctx *ctx, int n, int njob, const double *Q, const double *pi, double *Root, double *U,
                      double *V, int *sweeps);
 
+/* The whole Newton iteration of ONE branch on the device: the reference's "iterating a branch" loop of minbranches
+ * (src/treesub.c:8087-8108) -- lfuntdd at t, the direction p = -dl/|ddl| bounded to tb[], step quartering on lfunt until -lnL
+ * drops below l0, the convergence test with e, up to 10 rounds -- as a conditional WHILE graph whose body is the evaluation
+ * kernels plus a one-block step kernel.  One host->device copy, one graph launch and one device->host copy per branch.
+ * PRE: as pb200_branch_lnl.  t: current branch length; l0: current -lnL; first_cycle: icycle == 0 (border avoidance, :8098).
+ * out[4] = { t, -lnL(t), dl, ddl } as the loop leaves them (dl, ddl of the last lfuntdd: g_minbranches / varb_minbranches);
+ * *nevals (may be NULL) = evaluations done.  Same arithmetic as a host-driven loop over pb200_branch_lnl.               */
+int pb200_branch_newton(pb200_ctx *ctx, int nclass, const double *freqK, int a, int b, double t, double l0,
+                        const double *mult, const int *set_of_class, const double *pi, int semantics, int first_cycle,
+                        double e, const double tb[2], double out[4], int *nevals);
 /* The one-branch-at-a-time optimiser (`method = 1`: minbranches, src/treesub.c:8039-8123) needs what the evaluation
  * kernels never write: every internal node's conditional vectors, RESIDENT in HBM ([class][internal node][pattern]
  * [state], the layout of com.conP, src/treesub.c:3518-3530).

@@ -81,6 +81,16 @@ static int nccl_load()
 static const void* g_const_owner[64] = {nullptr};
 static unsigned long long g_const_gen[64] = {0};
 
+// launch parameters of one evaluation of the branch function (see prepare_branch)
+struct BranchLaunch {
+    bool dmma;
+    int NT, nclass, grid, nblk;
+    size_t smem;
+    Pt3FragParams qf; BranchDmmaParams pd;      // tensor path
+    Pt3Params qv; BranchParams pv;              // FP64-vector kernels (4 states)
+    size_t off_f, off_m, off_pi, off_s, off_st, off_r, total;
+};
+
 // ---- context ----
 struct DevBuf {
     void* p = nullptr;
@@ -131,6 +141,9 @@ struct pb200_ctx {
     size_t h_cstage_cap = 0;
     void* h_cbr = nullptr;      // pinned: per-call inputs of pb200_branch_lnl + its 3 results
     int cond_nclass = 0, cond_nscale = 0;
+    cudaGraph_t newton_graph = nullptr;          // pb200_branch_newton: WHILE graph of one branch's iteration
+    cudaGraphExec_t newton_exec = nullptr;
+    BranchLaunch newton_key;                     // the launch geometry / buffers the graph was captured with
     bool cond_dmma = false;     // the resident-vector kernels run on the DMMA path (n > 4; PB200_COND_DMMA=0 keeps the FP64-vector kernels)
     struct { int kind, nr, nset; long long set_stride; size_t off_sets; bool ok; } csets = {0, 0, 0, 0, 0, false};
     DevBuf d_eig;               // pb200_eigen_qrev: Q | pi | sets | info
@@ -207,6 +220,8 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->newton_exec) cudaGraphExecDestroy(c->newton_exec);
+    if (c->newton_graph) cudaGraphDestroy(c->newton_graph);
     for (int r = 0; r < 64; r++) if (c->peer_map[r]) cudaIpcCloseMemHandle(c->peer_map[r]);
     if (c->xchg) cudaFree(c->xchg);
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
@@ -1332,92 +1347,174 @@ extern "C" int pb200_cond_update(pb200_ctx* c, int nclass, int set_kind, int nr,
     return 0;
 }
 
-extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, int a, int b, double t, const double* mult,
-                                const int* set_of_class, const double* pi, int semantics, int want_dd, double out[3])
+// One evaluation of the branch function = P, P', P'' of the branch + the per-pattern sums.  The launch parameters are built
+// once (BranchLaunch) and used either directly (pb200_branch_lnl: a, b, t, want_dd by value) or inside the device-side
+// iteration (pb200_branch_newton: the kernels read them from the NewtonState in device memory, so that one captured graph
+// serves every branch).
+
+static int prepare_branch(pb200_ctx* c, int nclass, const double* freqK, int a, int b, double t, const double* mult,
+                          const int* set_of_class, const double* pi, int semantics, int want_dd, const char* who, BranchLaunch* L)
 {
-    if (!c || !mult || !set_of_class || !pi || !out) return fail("pb200_branch_lnl: null argument");
-    if (!c->d_cond.p || c->cond_nclass != nclass || !c->csets.ok) return fail("pb200_branch_lnl: pb200_cond_update must come first (same nclass)");
-    if (c->csets.kind != KIND_UVROOT && c->csets.kind != KIND_CIJK) return fail("pb200_branch_lnl: needs UVROOT or CIJK spectral sets");
-    if (semantics != BR_SEM_LFUNT && semantics != BR_SEM_SITECLASS) return fail("pb200_branch_lnl: bad semantics");
-    if (semantics == BR_SEM_SITECLASS && !freqK) return fail("pb200_branch_lnl: null freqK");
+    memset(L, 0, sizeof(*L));                    // (also the padding: the struct is compared bytewise as the graph's key)
+    if (!c || !mult || !set_of_class || !pi) return fail("%s: null argument", who);
+    if (!c->d_cond.p || c->cond_nclass != nclass || !c->csets.ok) return fail("%s: pb200_cond_update must come first (same nclass)", who);
+    if (c->csets.kind != KIND_UVROOT && c->csets.kind != KIND_CIJK) return fail("%s: needs UVROOT or CIJK spectral sets", who);
+    if (semantics != BR_SEM_LFUNT && semantics != BR_SEM_SITECLASS) return fail("%s: bad semantics", who);
+    if (semantics == BR_SEM_SITECLASS && !freqK) return fail("%s: null freqK", who);
     const int n = c->n, nnode = c->nnode, ns = c->ns;
-    if (a < ns || a >= nnode || b < 0 || b >= nnode || a == b) return fail("pb200_branch_lnl: bad branch %d..%d", a, b);
+    if (a < ns || a >= nnode || b < 0 || b >= nnode || a == b) return fail("%s: bad branch %d..%d", who, a, b);
     for (int k = 0; k < nclass; k++)
-        if (set_of_class[k] < 0 || set_of_class[k] >= c->csets.nset) return fail("pb200_branch_lnl: set_of_class[%d] out of range", k);
+        if (set_of_class[k] < 0 || set_of_class[k] >= c->csets.nset) return fail("%s: set_of_class[%d] out of range", who, k);
     CUDA_TRY(cudaSetDevice(c->device));
-    // per-call inputs: freqK | mult | pi | set_of_class ; results: 3 doubles
-    size_t off_f = 0, off_m = align16(off_f + (size_t)nclass * 8), off_pi = align16(off_m + (size_t)nclass * 8);
-    size_t off_s = align16(off_pi + (size_t)n * 8), off_r = align16(off_s + (size_t)nclass * 4), total = off_r + 32;
+    // per-call inputs: freqK | mult | pi | set_of_class | iteration state ; results: 3 doubles
+    L->off_f = 0; L->off_m = align16(L->off_f + (size_t)nclass * 8); L->off_pi = align16(L->off_m + (size_t)nclass * 8);
+    L->off_s = align16(L->off_pi + (size_t)n * 8); L->off_st = align16(L->off_s + (size_t)nclass * 4);
+    L->off_r = align16(L->off_st + sizeof(NewtonState)); L->total = L->off_r + 32;
+    if (L->total > (1 << 16)) return fail("%s: too many classes", who);
     if (!c->h_cbr) CUDA_TRY(cudaMallocHost(&c->h_cbr, 1 << 16));
-    if (total > (1 << 16)) return fail("pb200_branch_lnl: too many classes");
     const bool dmma = c->cond_dmma;
     const int NTP = (c->NT + 1) / 2;
     const long long p3stride = dmma ? (long long)c->KS * NTP * 64 : (long long)n * n;
-    long long ntile = dmma ? (c->npatt + 7) / 8 : (c->npatt + COND_TP - 1) / COND_TP;
+    const long long ntile = dmma ? (c->npatt + 7) / 8 : (c->npatt + COND_TP - 1) / COND_TP;
     const int tiles = (int)std::min<long long>(COND_TMAX, std::max<long long>(1, ntile / (2LL * c->nsm)));
-    int nblk;                                  // partial triples the final sum adds: blocks (vector kernels) or warps (tensor path)
-    int grid_dmma = 0;
-    if (dmma) {
-        grid_dmma = (int)std::min<long long>((ntile + 3) / 4, (long long)c->nsm * 3);
-        nblk = grid_dmma * 4;
-    }
-    else nblk = (int)((ntile + tiles - 1) / tiles);
-    if (c->d_cbr.ensure(total) || c->d_cP3.ensure((size_t)nclass * 3 * p3stride * 8) || c->d_cpart.ensure((size_t)nblk * 3 * 8) || c->d_cres.ensure(32))
+    L->dmma = dmma; L->NT = c->NT; L->nclass = nclass;
+    if (dmma) { L->grid = (int)std::min<long long>((ntile + 3) / 4, (long long)c->nsm * 3); L->nblk = L->grid * 4; }     // partials: one per warp
+    else      { L->grid = (int)((ntile + tiles - 1) / tiles); L->nblk = L->grid; }                                        // one per block
+    if (c->d_cbr.ensure(1 << 16) || c->d_cP3.ensure((size_t)nclass * 3 * p3stride * 8) || c->d_cpart.ensure((size_t)L->nblk * 3 * 8) || c->d_cres.ensure(32))
         return 1;
     char* hs = (char*)c->h_cbr;
     char* ds = (char*)c->d_cbr.p;
-    for (int k = 0; k < nclass; k++) ((double*)(hs + off_f))[k] = freqK ? freqK[k] : 1.0;
-    memcpy(hs + off_m, mult, (size_t)nclass * 8);
-    memcpy(hs + off_pi, pi, (size_t)n * 8);
-    memcpy(hs + off_s, set_of_class, (size_t)nclass * 4);
-    CUDA_TRY(cudaMemcpyAsync(ds, hs, off_r, cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < nclass; k++) ((double*)(hs + L->off_f))[k] = freqK ? freqK[k] : 1.0;
+    memcpy(hs + L->off_m, mult, (size_t)nclass * 8);
+    memcpy(hs + L->off_pi, pi, (size_t)n * 8);
+    memcpy(hs + L->off_s, set_of_class, (size_t)nclass * 4);
+    memset(&L->qf, 0, sizeof(L->qf)); memset(&L->pd, 0, sizeof(L->pd)); memset(&L->qv, 0, sizeof(L->qv)); memset(&L->pv, 0, sizeof(L->pv));
+    L->smem = 0;
     if (dmma) {
-        Pt3FragParams q;
+        Pt3FragParams& q = L->qf;
         q.n = n; q.kind = c->csets.kind; q.nr = c->csets.nr; q.nclass = nclass; q.NT = c->NT; q.KS = c->KS;
         q.set_stride = c->csets.set_stride; q.p3stride = p3stride;
-        q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + off_s);
-        q.mult = (const double*)(ds + off_m); q.t_dev = nullptr; q.t = t; q.out = (double*)c->d_cP3.p;
-        pt3_frag_kernel<<<nclass, 256, 0, c->stream>>>(q);
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
-        BranchDmmaParams p;
+        q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + L->off_s);
+        q.mult = (const double*)(ds + L->off_m); q.st = nullptr; q.t = t; q.out = (double*)c->d_cP3.p;
+        BranchDmmaParams& p = L->pd;
         p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.a = a; p.b = b; p.nscale = c->cond_nscale;
         p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride; p.ntiles = ntile; p.p3stride = p3stride;
         p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
-        p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
+        p.freqK = (const double*)(ds + L->off_f); p.pi = (const double*)(ds + L->off_pi); p.fpatt = (const double*)c->d_fpatt.p;
         p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
-        p.partial = (double*)c->d_cpart.p;
-        if (c->NT == 8) branch_dmma_kernel<8, 16><<<grid_dmma, 128, 0, c->stream>>>(p);
-        else            branch_dmma_kernel<3, 5><<<grid_dmma, 128, 0, c->stream>>>(p);
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
+        p.partial = (double*)c->d_cpart.p; p.st = nullptr;
     }
     else {
-        Pt3Params q;
+        Pt3Params& q = L->qv;
         q.n = n; q.kind = c->csets.kind; q.nr = c->csets.nr; q.nclass = nclass; q.set_stride = c->csets.set_stride;
-        q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + off_s);
-        q.mult = (const double*)(ds + off_m); q.t = t; q.out = (double*)c->d_cP3.p;
-        pt3_kernel<<<nclass, 256, 0, c->stream>>>(q);
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
-        BranchParams p;
+        q.sets = (const double*)((char*)c->d_cstage.p + c->csets.off_sets); q.set_of_class = (const int*)(ds + L->off_s);
+        q.mult = (const double*)(ds + L->off_m); q.t = t; q.st = nullptr; q.out = (double*)c->d_cP3.p;
+        BranchParams& p = L->pv;
         p.n = n; p.nclass = nclass; p.nnode = nnode; p.ns = ns; p.ncodes = c->ncodes; p.a = a; p.b = b; p.nscale = c->cond_nscale;
         p.semantics = semantics; p.want_dd = want_dd ? 1 : 0; p.npatt = c->npatt; p.zstride = c->zstride; p.tiles = tiles;
         p.P3 = (const double*)c->d_cP3.p; p.cond = (const double*)c->d_cond.p; p.scaleF = (const double*)c->d_cscale.p;
-        p.freqK = (const double*)(ds + off_f); p.pi = (const double*)(ds + off_pi); p.fpatt = (const double*)c->d_fpatt.p;
+        p.freqK = (const double*)(ds + L->off_f); p.pi = (const double*)(ds + L->off_pi); p.fpatt = (const double*)c->d_fpatt.p;
         p.z = (const unsigned char*)c->d_z.p; p.amb_n = (const unsigned char*)c->d_amb_n.p; p.amb_map = (const unsigned char*)c->d_amb_map.p;
-        p.partial = (double*)c->d_cpart.p;
-        const size_t smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * sizeof(double);
-        branch_kernel<<<nblk, COND_THREADS, smem, c->stream>>>(p);
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
+        p.partial = (double*)c->d_cpart.p; p.st = nullptr;
+        L->smem = (3 * (size_t)n * COND_LDP + 2 * (size_t)COND_TP * (n | 1) + 3 * 8 * COND_TP + 4 * COND_TMAX * COND_TP) * sizeof(double);
     }
-    cond_sum_kernel<<<1, 256, 0, c->stream>>>((const double*)c->d_cpart.p, nblk, (double*)c->d_cres.p);
+    return 0;
+}
+
+static int enqueue_branch_eval(pb200_ctx* c, const BranchLaunch& L, cudaStream_t s)
+{
+    if (L.dmma) {
+        pt3_frag_kernel<<<L.nclass, 256, 0, s>>>(L.qf);
+        CUDA_TRY(cudaGetLastError());
+        if (L.NT == 8) branch_dmma_kernel<8, 16><<<L.grid, 128, 0, s>>>(L.pd);
+        else           branch_dmma_kernel<3, 5><<<L.grid, 128, 0, s>>>(L.pd);
+    }
+    else {
+        pt3_kernel<<<L.nclass, 256, 0, s>>>(L.qv);
+        CUDA_TRY(cudaGetLastError());
+        branch_kernel<<<L.grid, COND_THREADS, L.smem, s>>>(L.pv);
+    }
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pb200_branch_lnl(pb200_ctx* c, int nclass, const double* freqK, int a, int b, double t, const double* mult,
+                                const int* set_of_class, const double* pi, int semantics, int want_dd, double out[3])
+{
+    if (!out) return fail("pb200_branch_lnl: null argument");
+    BranchLaunch L;
+    if (prepare_branch(c, nclass, freqK, a, b, t, mult, set_of_class, pi, semantics, want_dd, "pb200_branch_lnl", &L)) return 1;
+    char* hs = (char*)c->h_cbr;
+    char* ds = (char*)c->d_cbr.p;
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, L.off_st, cudaMemcpyHostToDevice, c->stream));
+    if (enqueue_branch_eval(c, L, c->stream)) return 1;
+    cond_sum_kernel<<<1, 256, 0, c->stream>>>((const double*)c->d_cpart.p, L.nblk, (double*)c->d_cres.p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(hs + off_r, c->d_cres.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(hs + L.off_r, c->d_cres.p, 24, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    memcpy(out, hs + off_r, 24);
+    memcpy(out, hs + L.off_r, 24);
+    return 0;
+}
+
+// The reference's "iterating a branch" loop (src/treesub.c:8087-8108: Newton direction from lfuntdd, step quartering on lfunt,
+// convergence test, up to 10 rounds) entirely on the device: the evaluation kernels and newton_step_kernel form the body of a
+// conditional WHILE graph node, so one branch costs one H2D copy (inputs + initial state), one graph launch and one D2H
+// copy (final state) however many evaluations it takes.  The graph is captured once per launch geometry and reused.
+extern "C" int pb200_branch_newton(pb200_ctx* c, int nclass, const double* freqK, int a, int b, double t, double l0, const double* mult,
+                                   const int* set_of_class, const double* pi, int semantics, int first_cycle, double e,
+                                   const double tb[2], double out[4], int* nevals)
+{
+    if (!out || !tb) return fail("pb200_branch_newton: null argument");
+    BranchLaunch L;
+    if (prepare_branch(c, nclass, freqK, a, b, t, mult, set_of_class, pi, semantics, 1, "pb200_branch_newton", &L)) return 1;
+    char* hs = (char*)c->h_cbr;
+    char* ds = (char*)c->d_cbr.p;
+    NewtonState* dst = (NewtonState*)(ds + L.off_st);
+    L.qf.st = dst; L.pd.st = dst; L.qv.st = dst; L.pv.st = dst;
+    // per-branch values live in the state, not in the captured parameters
+    L.qf.t = 0; L.qv.t = 0; L.pd.a = L.pd.b = L.pd.want_dd = 0; L.pv.a = L.pv.b = L.pv.want_dd = 0;
+    NewtonState st;
+    memset(&st, 0, sizeof(st));
+    st.t_eval = t; st.t = t; st.t0 = t; st.l = l0; st.l0 = l0; st.e = e; st.tb0 = tb[0]; st.tb1 = tb[1];
+    st.want_dd = 1; st.first_cycle = first_cycle ? 1 : 0; st.max_evals = 400; st.a = a; st.b = b;
+    memcpy(hs + L.off_st, &st, sizeof(st));
+    if (!c->newton_exec || memcmp(&c->newton_key, &L, sizeof(L)) != 0) {
+        if (c->newton_exec) { cudaGraphExecDestroy(c->newton_exec); c->newton_exec = nullptr; }
+        if (c->newton_graph) { cudaGraphDestroy(c->newton_graph); c->newton_graph = nullptr; }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaGraphCreate(&c->newton_graph, 0));
+        cudaGraphConditionalHandle handle;
+        CUDA_TRY(cudaGraphConditionalHandleCreate(&handle, c->newton_graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = handle; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+        cudaGraphNode_t node;
+        CUDA_TRY(cudaGraphAddNode(&node, c->newton_graph, nullptr, 0, &cp));
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        CUDA_TRY(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_branch_eval(c, L, c->stream);
+        if (!rc) {
+            newton_step_kernel<<<1, 256, 0, c->stream>>>((const double*)c->d_cpart.p, L.nblk, dst, handle);
+            if (cudaGetLastError() != cudaSuccess) rc = fail("pb200_branch_newton: capture failed");
+        }
+        cudaError_t ce = cudaStreamEndCapture(c->stream, nullptr);
+        if (rc) return 1;
+        if (ce != cudaSuccess) return fail("pb200_branch_newton: cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        CUDA_TRY(cudaGraphInstantiate(&c->newton_exec, c->newton_graph, 0));
+        c->newton_key = L;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ds, hs, L.off_r, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaGraphLaunch(c->newton_exec, c->stream));
+    c->launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(hs + L.off_st, ds + L.off_st, sizeof(NewtonState), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(&st, hs + L.off_st, sizeof(st));
+    if (!st.done) return fail("pb200_branch_newton: the device-side iteration did not finish");
+    if (st.nevals >= st.max_evals) return fail("pb200_branch_newton: no convergence within %d evaluations", st.max_evals);
+    out[0] = st.t; out[1] = st.l; out[2] = st.dl; out[3] = st.ddl;
+    if (nevals) *nevals = st.nevals;
+    c->launches += 3LL * (st.nevals - 1);
     return 0;
 }
 

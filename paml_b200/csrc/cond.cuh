@@ -131,6 +131,18 @@ __global__ void __launch_bounds__(COND_THREADS) cond_node_kernel(const CondNodeP
     }
 }
 
+// ---- the Newton iteration of one branch, kept on the device (pb200_branch_newton) ----
+// State of the reference's "iterating a branch" loop (src/treesub.c:8087-8108): the three kernels of one evaluation read what
+// to evaluate from it (t_eval, want_dd, a, b), newton_step_kernel sums their partials and advances it.
+struct NewtonState {
+    double t_eval;             // branch length of the next evaluation
+    double t, t0, l, l0, dl, ddl, p, step;
+    double e, tb0, tb1;        // convergence threshold, bounds of t
+    int want_dd;               // next evaluation: 1 = lfuntdd (value + derivatives), 0 = lfunt (value)
+    int icycleb, first_cycle, done, nevals, max_evals;
+    int a, b;                  // the branch b -> a
+};
+
 // ---- P, P', P'' of the branch being optimised ----
 struct Pt3Params {
     int n, kind, nr, nclass;
@@ -139,6 +151,7 @@ struct Pt3Params {
     const int* set_of_class;  // [nclass]
     const double* mult;       // [nclass] rgene * _rateSite * Qfactor (src/treesub.c:8435-8439)
     double t;
+    const NewtonState* st;    // device-side iteration: t is st->t_eval
     double* out;              // [nclass][3][n*n], each matrix COLUMN-major: [j*n + i] = P[i][j]
 };
 
@@ -149,10 +162,11 @@ __global__ void __launch_bounds__(256) pt3_kernel(const Pt3Params p)
     const double* set = p.sets + (size_t)p.set_of_class[cls] * p.set_stride;
     const int nroot = (p.kind == KIND_UVROOT) ? n : p.nr;
     const double* Root = set;
+    const double tt = p.st ? p.st->t_eval : p.t;
     if (tid < nroot) {
         const double m = __dmul_rn(p.mult[cls], Root[tid]);     // "multiply", src/treesub.c:8266
         mu[tid] = m;
-        ex[tid] = tid ? exp(__dmul_rn(p.t, m)) : 1.0;           // expt = 1 for the first root (src/treesub.c:8265-8267)
+        ex[tid] = tid ? exp(__dmul_rn(tt, m)) : 1.0;            // expt = 1 for the first root (src/treesub.c:8265-8267)
     }
     __syncthreads();
     double* o = p.out + (size_t)cls * 3 * n * n;
@@ -204,11 +218,14 @@ struct BranchParams {
     const unsigned char* amb_n;
     const unsigned char* amb_map;
     double* partial;           // [gridDim.x][3]
+    const NewtonState* st;     // device-side iteration: a, b, want_dd come from the state
 };
 
-__global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams p)
+__global__ void __launch_bounds__(COND_THREADS) branch_kernel(const BranchParams p0)
 {
     extern __shared__ __align__(16) double bsm[];
+    BranchParams p = p0;
+    if (p.st) { p.a = p.st->a; p.b = p.st->b; p.want_dd = p.st->want_dd; }
     const int n = p.n, LDT = n | 1, nm = p.want_dd ? 3 : 1, T = p.tiles;
     double* P3 = bsm;                           // [3][n][COND_LDP] TRANSPOSED: P3[m][j][i] = (d^m P)[i][j], rows i >= n zero
     double* tA = P3 + 3 * n * COND_LDP;         // [TP][LDT]
@@ -384,6 +401,57 @@ __global__ void __launch_bounds__(256) cond_sum_kernel(const double* partial, in
         __syncthreads();
     }
     if (tid < 3) out[tid] = s[tid][0];
+}
+
+// Sum of the block / warp partials in a fixed order, then one step of the reference's branch iteration (src/treesub.c:
+// 8087-8108): after a lfuntdd evaluation the Newton direction and the first trial step, after a lfunt evaluation accept /
+// quarter the step / give up, the convergence test, the next round.  Sets the graph's loop condition to 0 when the branch is done.
+__global__ void __launch_bounds__(256) newton_step_kernel(const double* partial, int nblk, NewtonState* st, cudaGraphConditionalHandle handle)
+{
+    __shared__ double s[3][256];
+    const int tid = threadIdx.x;
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < nblk; i += 256)
+        for (int m = 0; m < 3; m++) a[m] += partial[(size_t)i * 3 + m];
+    for (int m = 0; m < 3; m++) s[m][tid] = a[m];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) for (int m = 0; m < 3; m++) s[m][tid] += s[m][tid + o];
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    const double smallv = 1e-20;
+    bool try_step = false, done = false;
+    st->nevals++;
+    if (st->want_dd) {                                          // src/treesub.c:8088-8100
+        st->dl = s[1][0]; st->ddl = s[2][0];
+        const double p = -st->dl / fabs(st->ddl);
+        double step;
+        if (fabs(p) < smallv) step = 0;
+        else if (p < 0)       step = fmin(1.0, (st->tb0 - st->t0) / p);
+        else                  step = fmin(1.0, (st->tb1 - st->t0) / p);
+        if (st->first_cycle && step != 1 && step != 0) step *= 0.99;      // avoid border
+        st->p = p; st->step = step;
+        try_step = true;
+    }
+    else {                                                      // one trial of the step-halving loop, src/treesub.c:8101-8106
+        st->l = s[0][0];
+        if (st->l < st->l0) {
+            if (fabs(st->t - st->t0) < st->e * fabs(1 + st->t) && fabs(st->l - st->l0) < st->e) done = true;      // :8108
+            else {
+                st->t0 = st->t; st->l0 = st->l;
+                if (++st->icycleb < 10) { st->t_eval = st->t; st->want_dd = 1; }
+                else done = true;
+            }
+        }
+        else { st->step /= 4; try_step = true; }
+    }
+    if (try_step) {
+        if (st->step > smallv) { st->t = st->t0 + st->step * st->p; st->t_eval = st->t; st->want_dd = 0; }
+        else { st->t = st->t0; st->l = st->l0; done = true; }   // :8107
+    }
+    if (st->nevals >= st->max_evals) done = true;
+    if (done) { st->done = 1; cudaGraphSetConditional(handle, 0); }
 }
 
 }  // namespace pb200

@@ -123,12 +123,15 @@ struct BranchDmmaParams {
     const unsigned char* amb_n;
     const unsigned char* amb_map;
     double* partial;           // [gridDim.x * 4][3]: one triple per warp
+    const NewtonState* st;     // device-side iteration: a, b, want_dd come from the state
 };
 
 template <int NT, int KS>
-__global__ void __launch_bounds__(128, 3) branch_dmma_kernel(const BranchDmmaParams p)
+__global__ void __launch_bounds__(128, 3) branch_dmma_kernel(const BranchDmmaParams p0)
 {
     constexpr int NTP = (NT + 1) / 2;
+    BranchDmmaParams p = p0;
+    if (p.st) { p.a = p.st->a; p.b = p.st->b; p.want_dd = p.st->want_dd; }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int n = p.n, nm = p.want_dd ? 3 : 1;
     const long long N = p.npatt;
@@ -244,7 +247,7 @@ struct Pt3FragParams {
     const double* sets;
     const int* set_of_class;
     const double* mult;
-    const double* t_dev;      // the branch length is read from device memory when t_dev != nullptr (device-side Newton iteration)
+    const NewtonState* st;    // device-side iteration: t is st->t_eval
     double t;
     double* out;              // [nclass][3][p3stride]
 };
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256) pt3_frag_kernel(const Pt3FragParams p)
     const double* set = p.sets + (size_t)p.set_of_class[cls] * p.set_stride;
     const int nroot = (p.kind == KIND_UVROOT) ? n : p.nr;
     const double* Root = set;
-    const double tt = p.t_dev ? *p.t_dev : p.t;
+    const double tt = p.st ? p.st->t_eval : p.t;
     if (tid < nroot) {
         const double m = __dmul_rn(p.mult[cls], Root[tid]);     // "multiply", src/treesub.c:8266
         mu[tid] = m;

@@ -191,6 +191,21 @@ class TreeLikelihood:
                                        C.c_int(semantics), C.c_int(1 if want_dd else 0), _ptr(out, C.c_double)))
         return out
 
+    def branch_newton(self, freqK, a, b, t, l0, mult, set_of_class, pi, semantics, first_cycle=False, e=1e-6, tb=(1e-8, 50.0)):
+        """pb200_branch_newton -> (t, -lnL, dl, ddl, number of evaluations): the whole iteration of one branch on the device."""
+        mult = np.ascontiguousarray(mult, np.float64)
+        soc = np.ascontiguousarray(set_of_class, np.int32)
+        pi = np.ascontiguousarray(pi, np.float64)
+        fk = None if freqK is None else np.ascontiguousarray(freqK, np.float64)
+        tbv = np.ascontiguousarray(tb, np.float64)
+        out = np.zeros(4)
+        nev = C.c_int(0)
+        check(self._L.pb200_branch_newton(self._ctx, C.c_int(mult.shape[0]), _ptr(fk, C.c_double), C.c_int(a), C.c_int(b),
+                                          C.c_double(float(t)), C.c_double(float(l0)), _ptr(mult, C.c_double), _ptr(soc, C.c_int),
+                                          _ptr(pi, C.c_double), C.c_int(semantics), C.c_int(1 if first_cycle else 0), C.c_double(float(e)),
+                                          _ptr(tbv, C.c_double), _ptr(out, C.c_double), C.byref(nev)))
+        return out[0], out[1], out[2], out[3], nev.value
+
     def cond_get(self, node):
         """Resident vectors of one internal node [nclass, npatt, n] and the scale factors [nclass, nscale, npatt]."""
         cond = np.zeros((self.cond_nclass, self.npatt, self.n))

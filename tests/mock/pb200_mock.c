@@ -311,6 +311,36 @@ int pb200_p2p_init(pb200_ctx *c, int nranks, int rank, const char *handles) { (v
 int pb200_p2p_enable(pb200_ctx *c, int enable) { (void)c; (void)enable; return fail("no peer memory in the mock"); }
 int pb200_set_timing(pb200_ctx *c, int enable) { (void)c; (void)enable; return 0; }
 int pb200_last_timing(pb200_ctx *c, double ms[5]) { (void)c; memset(ms, 0, 5 * sizeof(double)); return 0; }
+/* the branch iteration (src/treesub.c:8087-8108) as a plain host loop over the mock's own pb200_branch_lnl */
+int pb200_branch_newton(pb200_ctx *c, int nclass, const double *freqK, int a, int b, double t, double l0, const double *mult,
+                        const int *set_of_class, const double *pi, int semantics, int first_cycle, double e, const double tb[2],
+                        double out[4], int *nevals)
+{
+   double t0 = t, l = l0, dl = 0, ddl = -1, p, step, o[3], smallv = 1e-20;
+   int icycleb, i, nev = 0;
+   for (icycleb = 0; icycleb < 10; icycleb++) {
+      if (pb200_branch_lnl(c, nclass, freqK, a, b, t, mult, set_of_class, pi, semantics, 1, o)) return 1;
+      nev++; dl = o[1]; ddl = o[2];
+      p = -dl / fabs(ddl);
+      if (fabs(p) < smallv) step = 0;
+      else if (p < 0)       step = (1 < (tb[0] - t0) / p ? 1 : (tb[0] - t0) / p);
+      else                  step = (1 < (tb[1] - t0) / p ? 1 : (tb[1] - t0) / p);
+      if (first_cycle && step != 1 && step != 0) step *= 0.99;
+      for (i = 0; step > smallv; i++, step /= 4) {
+         t = t0 + step * p;
+         if (pb200_branch_lnl(c, nclass, freqK, a, b, t, mult, set_of_class, pi, semantics, 0, o)) return 1;
+         nev++; l = o[0];
+         if (l < l0) break;
+      }
+      if (step <= smallv) { t = t0; l = l0; break; }
+      if (fabs(t - t0) < e * fabs(1 + t) && fabs(l - l0) < e) break;
+      t0 = t; l0 = l;
+   }
+   out[0] = t; out[1] = l; out[2] = dl; out[3] = ddl;
+   if (nevals) *nevals = nev;
+   return 0;
+}
+
 long long pb200_launch_count(pb200_ctx *c) { return c ? c->launches : -1; }
 const char *pb200_last_kernel(pb200_ctx *c) { return "mock (CPU oracle, tests only)"; }
 int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons, const unsigned char *scale_flags, int *prog, int cap, int *nslots)

@@ -216,3 +216,64 @@ def test_branch_derivatives_against_reference_lfuntdd(path, dmma, monkeypatch):
     assert abs(out[0] - r["l"]) <= 1e-10 * abs(r["l"]), (out[0], r["l"])
     assert abs(out[1] - r["dl"]) <= 1e-8 * max(1.0, abs(r["dl"])) + 1e-10 * abs(r["ddl"]), (out[1], r["dl"])
     assert abs(out[2] - r["ddl"]) <= 1e-8 * abs(r["ddl"]), (out[2], r["ddl"])
+
+
+def _host_branch_iteration(t_, p, r, mult, sem, l0, first_cycle, e, tb=(1e-8, 50.0)):
+    """The reference's "iterating a branch" loop (src/treesub.c:8087-8108) driven from the host over pb200_branch_lnl."""
+    a, b = r["a"], r["b"]
+    t = t0 = r["t"]
+    l = l0
+    dl, ddl, nev = 0.0, -1.0, 0
+    small = 1e-20
+    for _ in range(10):
+        o = t_.branch_lnl(p.freqK, a, b, t, mult, p.branch_set[:, a], p.pi[:p.n], sem, True); nev += 1
+        dl, ddl = o[1], o[2]
+        pp = -dl / abs(ddl)
+        if abs(pp) < small:
+            step = 0.0
+        elif pp < 0:
+            step = min(1.0, (tb[0] - t0) / pp)
+        else:
+            step = min(1.0, (tb[1] - t0) / pp)
+        if first_cycle and step != 1 and step != 0:
+            step *= 0.99
+        while step > small:
+            t = t0 + step * pp
+            l = t_.branch_lnl(p.freqK, a, b, t, mult, p.branch_set[:, a], p.pi[:p.n], sem, False)[0]; nev += 1
+            if l < l0:
+                break
+            step /= 4
+        if step <= small:
+            t, l = t0, l0
+            break
+        if abs(t - t0) < e * abs(1 + t) and abs(l - l0) < e:
+            break
+        t0, l0 = t, l
+    return t, l, dl, ddl, nev
+
+
+@pytest.mark.parametrize("path", BRANCH_FIXTURES, ids=[_os.path.basename(f)[:-5] for f in BRANCH_FIXTURES])
+@pytest.mark.parametrize("first_cycle", [True, False])
+def test_branch_newton_on_device_equals_host_driven_loop(path, first_cycle):
+    """pb200_branch_newton (the iteration of one branch as a device-side WHILE graph) must take exactly the steps of the
+    reference's loop driven from the host over single evaluations: same t, -lnL, dl, ddl to the bit, same evaluation count.
+    Run twice on the same context (the captured graph is reused) and from a displaced start (several Newton rounds)."""
+    p = load_fixture(path)
+    r = dict(p.branch_rec)
+    a, b = r["a"], r["b"]
+    t_ = TreeLikelihood(0)
+    t_.set_problem(p)
+    sons = _sons(p)
+    own = dict(sons); own[b] = [c for c in sons[b] if c != a]
+    t_.cond_update(p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, _postorder(p, a, sons) + _postorder(p, b, own),
+                   p.scale_flags if p.nscale else None)
+    mult = p.branch_t[:, a] / r["branch_len"]
+    sem = 1 if r["siteclass"] else 0
+    for start in (r["t"], 3.0 * r["t"] + 0.05):
+        r["t"] = start
+        l0 = t_.branch_lnl(p.freqK, a, b, start, mult, p.branch_set[:, a], p.pi[:p.n], sem, False)[0]
+        want = _host_branch_iteration(t_, p, r, mult, sem, l0, first_cycle, 1e-6)
+        got = t_.branch_newton(p.freqK, a, b, start, l0, mult, p.branch_set[:, a], p.pi[:p.n], sem, first_cycle, 1e-6)
+        assert got[4] == want[4] and got[4] >= 2, (got, want)
+        assert got[:4] == want[:4], (got, want)
+    t_.close()
