@@ -447,7 +447,8 @@ __global__ void __launch_bounds__(256) newton_step_kernel(const double* partial,
         else { st->step /= 4; try_step = true; }
     }
     if (try_step) {
-        if (st->step > smallv) { st->t = st->t0 + st->step * st->p; st->t_eval = st->t; st->want_dd = 0; }
+        // (unfused multiply-add: the host compiler of the reference does not contract t0 + step * p either)
+        if (st->step > smallv) { st->t = __dadd_rn(st->t0, __dmul_rn(st->step, st->p)); st->t_eval = st->t; st->want_dd = 0; }
         else { st->t = st->t0; st->l = st->l0; done = true; }   // :8107
     }
     if (st->nevals >= st->max_evals) done = true;
