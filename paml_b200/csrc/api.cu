@@ -428,6 +428,9 @@ static int pick_launch(int NT, int mt_small, PruneLaunch* L)
     const char* wenv = getenv("PB200_MAXW");         // tuning: register budget for 20 / 24 resident warps per SM (102 / 85 registers)
     if (NT == 8 && mt_small && wenv && atoi(wenv) == 20) { *L = make_launch<8, 16, 1, 20>(); return 0; }
     if (NT == 8 && mt_small && wenv && atoi(wenv) == 24) { *L = make_launch<8, 16, 1, 24>(); return 0; }
+    const char* aenv = getenv("PB200_AA_MT");        // tuning: patterns per warp / 8 of the amino-acid shape
+    if (NT == 3 && aenv && atoi(aenv) == 4) { *L = make_launch<3, 5, 4, 12>(); return 0; }
+    if (NT == 3 && aenv && atoi(aenv) == 3) { *L = make_launch<3, 5, 3, 16>(); return 0; }
     if (NT == 8) *L = mt_small ? make_launch<8, 16, 1, 16>() : make_launch<8, 16, 2, 8>();
     else if (NT == 3) *L = mt_small ? make_launch<3, 5, 1, 16>() : make_launch<3, 5, 2, 16>();
     else if (NT == 1) *L = mt_small ? make_launch<1, 1, 1, 16>() : make_launch<1, 1, 4, 16>();
@@ -453,6 +456,14 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     // than 16 x 8; the small alphabets keep more patterns per warp.  PB200_MT_SMALL=0/1 overrides.
     const char* mtenv = getenv("PB200_MT_SMALL");
     const int small0 = mtenv ? (atoi(mtenv) ? 1 : 0) : (c->NT == 8 ? 1 : 0);
+    if (c->NT == 3 && !mtenv && !getenv("PB200_AA_MT")) {
+        // amino-acid shape: a child's contraction is only 15 DMMAs per 8 patterns, so the walk's per-op overhead weighs more
+        // than at 61 states: 32 patterns per warp amortise it (0.57 against 0.54 of the DMMA peak on config 4) as long as
+        // three 4-warp CTAs still fit an SM's shared memory
+        PruneLaunch L4 = make_launch<3, 5, 4, 12>();
+        const size_t pw4 = align16((size_t)c->plan.nslots * L4.slot_doubles * sizeof(double) + L4.ring_bytes);
+        if (64 + 4 * pw4 <= (size_t)75 * 1024) { L = L4; per_warp = pw4; warps = 4; }
+    }
     for (int small = small0; small < 2 && warps == 0; small++) {
         if (pick_launch(c->NT, small, &L)) return 1;
         per_warp = align16((size_t)c->plan.nslots * L.slot_doubles * sizeof(double) + L.ring_bytes);
@@ -507,7 +518,12 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
         double dmma_per_child = (double)c->KS * c->NT * (L.rows / 8);
         double cycles = (double)c->plan.n_internal_children * dmma_per_child * 16.0;
         p.stagger_ns = senv ? (unsigned int)atol(senv) : (unsigned int)std::min(2.0e6, cycles / 1.9);
-        if (warps <= 4) p.stagger_ns = 0;
+        p.stagger_ctas = 0;
+        if (warps <= 4) {
+            const char* cenv = getenv("PB200_STAGGER_CTAS");       // tuning: stagger the CTAs of an SM (see kernel); default off
+            if (cenv && atoi(cenv) > 0) p.stagger_ctas = -1;       // resolved below, once the grid is known
+            else p.stagger_ns = 0;
+        }
     }
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, warps * 32, smem));
@@ -530,6 +546,10 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     const char* genv = getenv("PB200_GRID");
     if (genv && atoi(genv) > 0) grid = atoi(genv);
     if (grid < 1) grid = 1;
+    if (p.stagger_ctas < 0) {
+        p.stagger_ctas = std::max(1, std::min(per_sm, grid / std::max(1, c->nsm)));
+        if (p.stagger_ctas < 2) { p.stagger_ctas = 0; p.stagger_ns = 0; }
+    }
     kfn<<<grid, warps * 32, smem, c->stream>>>(p);
     snprintf(c->last_kernel, sizeof(c->last_kernel), "prune_kernel<%d,%d,%d,%d,%s> grid %d x %d threads, %zu B smem", c->NT, c->KS,
              L.rows / 8, L.max_warps, p.prog_in_const ? "true" : "false", grid, warps * 32, smem);

@@ -277,6 +277,7 @@ struct PruneParams {
     unsigned int* tile_counter; // dynamic work distribution (reset by mix_kernel)
     int warp_smem_bytes;        // shared memory per warp: slots + tip-code ring
     unsigned int stagger_ns;    // start delay between the warps that share an SM sub-partition (see kernel)
+    int stagger_ctas;           // > 0: CTAs of 4 warps, this many per SM: the delay goes by the CTA's slot (blockIdx.x / SMs) instead
     int pipe_lock;              // n > 0: at most n warps of a sub-partition inside a DMMA block at once (tuning aid)
     int static_items;           // 1: items dealt round-robin to warps; 0: atomic work counter
     int prefetch_b;             // 1: prefetch.global.L1 the next op's B-fragment tiles one op ahead
@@ -393,7 +394,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
     // lockstep -- all gathering tips at once, then all queueing on the tensor pipe -- and the phases simply add
     // up.  Starting them one pipe-phase apart lets one warp's tip gathers/stores run under another's DMMAs.
     if (p.stagger_ns) {
-        unsigned long long wait_ns = (unsigned long long)(warp >> 2) * p.stagger_ns;
+        // (4-warp CTAs: the warps that share a sub-partition belong to different CTAs; the first wave is dealt breadth-first over
+        //  the SMs, so blockIdx.x / gridDim-per-wave is the CTA's slot on its SM)
+        unsigned long long wait_ns = (unsigned long long)(p.stagger_ctas > 0 ? (blockIdx.x / (gridDim.x / p.stagger_ctas)) % p.stagger_ctas : (warp >> 2)) * p.stagger_ns;
         while (wait_ns > 0) { unsigned int chunk = wait_ns > 500000ull ? 500000u : (unsigned int)wait_ns; __nanosleep(chunk); wait_ns -= chunk; }
     }
 

@@ -76,6 +76,19 @@ if what == "nuc2":
          ("v2 ppt8 64x4 (P in smem)", dict(PB200_NUC_PPT="84", PB200_NUC_PCONST="0")),
          ("v2 ppt6 128x2 (P in smem)", dict(PB200_NUC_PPT="6", PB200_NUC_PCONST="0"))]
     sweep("cfg5", p, V, dfma)
+if what == "aa2":
+    p = simulate.aa_gamma_problem(npatt=200_000, wag=True)
+    V = [("default (MT=2)", dict()), ("MT=3", dict(PB200_AA_MT="3")), ("MT=4", dict(PB200_AA_MT="4")),
+         ("MT=4, 8-warp CTAs", dict(PB200_AA_MT="4", PB200_WARPS="8")), ("MT=3, 8-warp CTAs", dict(PB200_AA_MT="3", PB200_WARPS="8")),
+         ("MT=4, smem 227", dict(PB200_AA_MT="4", PB200_SMEM_KB="227", PB200_WARPS="12"))]
+    sweep("cfg4", p, V, dmma)
+if what == "codon3":
+    p = simulate.codon_m0_problem(npatt=100_000, seed=13147)
+    V = [("default", dict())] + [("stagger CTAs %d ns" % ns, dict(PB200_STAGGER_CTAS="1", PB200_STAGGER_NS=str(ns))) for ns in (500, 1000, 2000, 4000, 8000, 16000)]
+    V += [("16-warp CTA stagger %d ns" % ns, dict(PB200_WARPS="16", PB200_STAGGER_NS=str(ns))) for ns in (1000, 4000)]
+    sweep("cfg2", p, V, dmma)
+    p = simulate.codon_sites_problem(npatt=50_000, seed=13149, freqs=(0.4, 0.3, 0.2, 0.1), omegas=(0.05, 0.3, 1.0, 2.5))
+    sweep("cfg3_K4", p, V[:5], dmma)
 if what == "codon2":
     p = simulate.codon_m0_problem(npatt=100_000, seed=13147)
     V = [("default", dict()), ("regs for 20 warps/SM", dict(PB200_MAXW="20")), ("regs for 24 warps/SM", dict(PB200_MAXW="24"))]
