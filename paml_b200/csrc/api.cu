@@ -1444,7 +1444,7 @@ static int prepare_branch(pb200_ctx* c, int nclass, const double* freqK, int a, 
 static int enqueue_branch_eval(pb200_ctx* c, const BranchLaunch& L, cudaStream_t s)
 {
     if (L.dmma) {
-        pt3_frag_kernel<<<L.nclass, 256, 0, s>>>(L.qf);
+        pt3_frag_kernel<<<dim3(L.nclass, (unsigned)((L.qf.p3stride + 255) / 256)), 256, 0, s>>>(L.qf);
         CUDA_TRY(cudaGetLastError());
         if (L.NT == 8) branch_dmma_kernel<8, 16><<<L.grid, 128, 0, s>>>(L.pd);
         else           branch_dmma_kernel<3, 5><<<L.grid, 128, 0, s>>>(L.pd);

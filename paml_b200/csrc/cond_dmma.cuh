@@ -269,7 +269,9 @@ __global__ void __launch_bounds__(256) pt3_frag_kernel(const Pt3FragParams p)
     const int NTP = (p.NT + 1) / 2;
     double* o = p.out + (size_t)cls * 3 * p.p3stride;
     const int total = p.KS * NTP * 64;
-    for (int e0 = tid; e0 < total; e0 += 256) {
+    // grid.y blocks share the matrix: one element (and its n-term sum) per thread -- a single block per class made this kernel
+    // the longest of a Newton step on small data (100 us at n = 61 whatever the number of patterns)
+    for (int e0 = blockIdx.y * 256 + tid; e0 < total; e0 += gridDim.y * 256) {
         const int e = e0 & 1, lane = (e0 >> 1) & 31, f = e0 >> 6, pr = f % NTP, ks = f / NTP;
         const int i = 8 * (2 * pr + e) + (lane >> 2), j = 4 * ks + (lane & 3);
         double P = 0.0, dP = 0.0, ddP = 0.0;

@@ -12,7 +12,11 @@ npatt = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 p = simulate.codon_m0_problem(ns=ns, npatt=npatt, seed=91)
 rows = (("unmodified reference (1 core)", REPO + "/oracle/_ref/codeml", {}),
         ("drop-in, minbranches on the CPU (PB200_MINB=0)", REPO + "/paml_b200/bin/codeml_b200", {"PB200_MINB": "0"}),
-        ("drop-in, minbranches on the GPU", REPO + "/paml_b200/bin/codeml_b200", {}))
+        ("drop-in, minbranches on the GPU, FP64-vector kernels, host-driven Newton (round 1)", REPO + "/paml_b200/bin/codeml_b200", {"PB200_COND_DMMA": "0", "PB200_NEWTON": "host"}),
+        ("drop-in, minbranches on the GPU, tensor-path kernels, host-driven Newton", REPO + "/paml_b200/bin/codeml_b200", {"PB200_NEWTON": "host"}),
+        ("drop-in, minbranches on the GPU, tensor-path kernels, device-side Newton (default)", REPO + "/paml_b200/bin/codeml_b200", {}))
+if len(sys.argv) > 3 and sys.argv[3] == "gpu":
+    rows = rows[2:]
 for tag, exe, env in rows:
     if not os.path.exists(exe):
         continue
@@ -25,4 +29,4 @@ for tag, exe, env in rows:
                        text=True, env=dict(os.environ, **env))
     dt = time.time() - t0
     l = re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d + "/mlc").read()) if r.returncode == 0 else []
-    print("%-50s %8.2f s   lnL %s   (%d taxa, %d codon patterns)" % (tag, dt, l[-1] if l else "FAILED rc=%d" % r.returncode, ns, int(p.npatt)))
+    print("%-86s %8.2f s   lnL %s   (%d taxa, %d codon patterns)" % (tag, dt, l[-1] if l else "FAILED rc=%d" % r.returncode, ns, int(p.npatt)))
