@@ -26,7 +26,10 @@ for tag, exe, env in rows:
                              extra=dict(fix_kappa=0, fix_omega=0, fix_blength=1, method=1))
     t0 = time.time()
     r = subprocess.run([exe, "run.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True, env=dict(os.environ, **env))
+                       text=True, env=dict(os.environ, PB200_PROFILE="1", PB200_TEST_SEED="20261017",
+                                           **(dict(env, LD_PRELOAD=REPO + "/oracle/_ref/libfixedseed.so") if "_ref/" in exe else env)))
     dt = time.time() - t0
     l = re.findall(r"lnL\(ntime:\s*\d+\s+np:\s*\d+\):\s*(-?[\d.]+)", open(d + "/mlc").read()) if r.returncode == 0 else []
-    print("%-86s %8.2f s   lnL %s   (%d taxa, %d codon patterns)" % (tag, dt, l[-1] if l else "FAILED rc=%d" % r.returncode, ns, int(p.npatt)))
+    m = re.search(r"minbranches (\d+) calls, ([\d.]+) s in all, (\d+) branch iterations \(([\d.]+) us each\), (\d+) branch-function evaluations", r.stdout)
+    prof = ("  | minbranches: %s s in %s calls, %s evaluations" % (m.group(2), m.group(1), m.group(5))) if m else ""
+    print("%-86s %8.2f s wall  lnL %s   (%d taxa, %d codon patterns)%s" % (tag, dt, l[-1] if l else "FAILED rc=%d" % r.returncode, ns, int(p.npatt), prof))
