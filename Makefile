@@ -30,7 +30,7 @@ $(BIN)/codeml_b200: $(HOST)/codeml_b200.c $(HOST)/wrap_b200.inc $(HOST)/plfun_b2
 $(BIN)/baseml_b200: $(HOST)/baseml_b200.c $(HOST)/wrap_b200.inc $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
 	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/baseml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
 
-$(LIB): $(CSRC)/api.cu $(CSRC)/kernels.cuh $(CSRC)/patterns.cpp $(CSRC)/plan.cpp $(CSRC)/plan.h $(CSRC)/prune4.cuh $(CSRC)/prune4v2.cuh $(CSRC)/prune_tma.cuh $(CSRC)/eigen.cuh $(CSRC)/cond.cuh include/paml_b200.h
+$(LIB): $(CSRC)/api.cu $(CSRC)/kernels.cuh $(CSRC)/patterns.cpp $(CSRC)/plan.cpp $(CSRC)/plan.h $(CSRC)/prune4.cuh $(CSRC)/prune4v2.cuh $(CSRC)/prune_tma.cuh $(CSRC)/prune_ps.cuh $(CSRC)/cond_dmma.cuh $(CSRC)/eigen.cuh $(CSRC)/cond.cuh include/paml_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/api.cu $(CSRC)/plan.cpp $(CSRC)/patterns.cpp -ldl 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
 	@grep -E "error|warning" build_ptxas.log || true
 

@@ -196,6 +196,9 @@ const char *pb200_last_kernel(pb200_ctx *ctx);
  * of on-chip slots (conditional-vector tiles live at once) in *nslots.                                   */
 int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons,
                     const unsigned char *scale_flags, int *prog, int cap, int *nslots);
+/* The same for the P-stationary kernel of the 61..64-state shape (csrc/plan.h, PlanPS; csrc/prune_ps.cuh). */
+int pb200_plan_tree_ps(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons,
+                       const unsigned char *scale_flags, int *prog, int cap, int *nslots);
 /* The same for the 4-state kernel's macro-op program (csrc/plan.h, Plan4): ops[2 ints per macro-op] and the order
  * in which the walk consumes the tips.  Returns the number of op ints (negative on error); *ntip_out = tips.  */
 int pb200_plan_tree4(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons,

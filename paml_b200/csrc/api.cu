@@ -14,6 +14,7 @@
 #include "../../include/paml_b200.h"
 #include "kernels.cuh"
 #include "prune_tma.cuh"
+#include "prune_ps.cuh"
 #include "prune4.cuh"
 #include "prune4v2.cuh"
 #include "eigen.cuh"
@@ -132,6 +133,11 @@ struct pb200_ctx {
     int nnode = 0, root = -1;
     Plan plan;
     unsigned long long plan_gen = 0;
+    PlanPS planps;              // program of the P-stationary kernel (prune_ps.cuh; 61..64-state shape only)
+    unsigned long long plan_gen_ps = 0;
+    int ps_banks = 1;
+    int ps_mt = 0;              // > 0: evaluations run prune_ps_kernel<ps_mt> (P(t), tip rows and pi in LOGICAL state order)
+    DevBuf d_prog_ps;
     DevBuf d_prog;
     // eval
     DevBuf d_stage, d_P, d_fhK, d_lnf, d_partial, d_counter, d_result, d_flush, d_item_partial;
@@ -299,7 +305,7 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
         if (c->d_amb_mask.ensure(256)) return 1;
         CUDA_TRY(cudaMemcpy(c->d_amb_mask.p, mask.data(), 256, cudaMemcpyHostToDevice));
     }
-    if (ns != c->ns) { c->nnode = 0; c->root = -1; c->plan = Plan(); c->plan4 = Plan4(); }   // the plan was built for another tip count: pb200_set_tree must follow
+    if (ns != c->ns) { c->nnode = 0; c->root = -1; c->plan = Plan(); c->plan4 = Plan4(); c->planps = PlanPS(); c->ps_mt = 0; }   // the plan was built for another tip count: pb200_set_tree must follow
     c->n = n; c->ns = ns; c->npatt = npatt; c->zstride = zstride; c->cleandata = cleandata; c->ncodes = ncodes;
     choose_shape(n, &c->NT, &c->KS);
     c->ld = 4 * c->KS;
@@ -324,6 +330,17 @@ extern "C" int pb200_plan_tree(int nnode, int ns, int root, const int* nson, con
     std::string err = plan_tree(nnode, ns, root, nson, sons, maxsons, scale_flags, pl);
     if (!err.empty()) { fail("%s", err.c_str()); return -1; }
     if (nslots) *nslots = pl.nslots;
+    if (prog) for (int i = 0; i < cap && i < (int)pl.prog.size(); i++) prog[i] = pl.prog[i];
+    return (int)pl.prog.size();
+}
+
+extern "C" int pb200_plan_tree_ps(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                                  const unsigned char* scale_flags, int* prog, int cap, int* nslots)
+{
+    PlanPS pl;
+    std::string err = plan_tree_ps(nnode, ns, root, nson, sons, maxsons, scale_flags, pl);
+    if (!err.empty()) { fail("%s", err.c_str()); return -1; }
+    if (nslots) *nslots = pl.nD + pl.nG;
     if (prog) for (int i = 0; i < cap && i < (int)pl.prog.size(); i++) prog[i] = pl.prog[i];
     return (int)pl.prog.size();
 }
@@ -397,6 +414,32 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
     static unsigned long long gen_counter = 0;
     c->cond_nclass = 0; c->csets.ok = false;               // resident conditional vectors belong to the previous topology
     c->plan = pl; c->nnode = nnode; c->root = root; c->plan_gen = ++gen_counter;
+    c->ps_mt = 0;
+    if (c->NT == 8 && c->KS == 16 && !c->nuc4) {
+        // P-stationary kernel: chunks of 64 patterns when two CTAs' slots fit an SM's shared memory, else 32
+        const char* kenv = getenv("PB200_KERNEL");
+        const char* menv = getenv("PB200_PS_MT");
+        PlanPS ps;
+        err = plan_tree_ps(nnode, c->ns, root, nson, sons, maxsons, scale_flags, ps);    // fails for shapes the kernel does not cover
+        // chunks of 64 patterns when the slots fit an SM's shared memory (two banks of G slots preferred), else 32
+        int mt = 0, banks = 0;
+        if (err.empty()) {
+            const size_t cap = (size_t)227 * 1024;
+            const int mt_try[4] = {8, 4, 8, 4}, bk_try[4] = {2, 2, 1, 1};
+            for (int i = 0; i < 4 && !mt; i++) {
+                if (menv && atoi(menv) != mt_try[i]) continue;
+                const size_t need = mt_try[i] == 8 ? PsCfg<8>::smem_bytes(ps.nD, ps.nG, bk_try[i], ps.ntip, ps.n_dops) : PsCfg<4>::smem_bytes(ps.nD, ps.nG, bk_try[i], ps.ntip, ps.n_dops);
+                if (need <= cap) { mt = mt_try[i]; banks = bk_try[i]; }
+            }
+        }
+        const bool want = kenv ? strcmp(kenv, "ps") == 0 : false;
+        if (want && mt) {
+            if (c->d_prog_ps.ensure(ps.prog.size() * sizeof(int))) return 1;
+            CUDA_TRY(cudaMemcpyAsync(c->d_prog_ps.p, ps.prog.data(), ps.prog.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            c->planps = ps; c->plan_gen_ps = ++gen_counter; c->ps_mt = mt; c->ps_banks = banks;
+        }
+    }
     c->have_eval = false;
     return 0;
 }
@@ -556,6 +599,50 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// ---- P-stationary pruning kernel (prune_ps.cuh) ----
+template <int MT>
+static int launch_prune_ps_t(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    PrunePsParams p;
+    p.prog = (const int*)c->d_prog_ps.p;
+    bool in_const = false;
+    if (c->planps.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
+        if (g_const_owner[c->device] != c || g_const_gen[c->device] != c->plan_gen_ps) {
+            if (g_const_owner[c->device] && g_const_owner[c->device] != c) CUDA_TRY(cudaDeviceSynchronize());   // another context may be using it
+            CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, c->planps.prog.data(), c->planps.prog.size() * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+            g_const_owner[c->device] = c; g_const_gen[c->device] = c->plan_gen_ps;
+        }
+        in_const = true;
+    }
+    void (*kfn)(const PrunePsParams) = in_const ? prune_ps_kernel<MT, true> : prune_ps_kernel<MT, false>;
+    const size_t smem = PsCfg<MT>::smem_bytes(c->planps.nD, c->planps.nG, c->ps_banks, c->planps.ntip, c->planps.n_dops);
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.z = (const unsigned char*)c->d_z.p;
+    p.zstride = c->zstride; p.npatt = c->npatt;
+    p.ntile = (c->npatt + 7) / 8;
+    p.nunits = p.ntile * nclass;
+    p.Pbuf = (const double*)c->d_P.p; p.pstride = c->pstride;
+    p.nnode = c->nnode; p.nclass = nclass; p.n = c->n;
+    p.semantics = semantics; p.nscale = c->planps.nscale;
+    p.nbanks = c->ps_banks; p.ntip = c->planps.ntip;
+    p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
+    // one CTA per SM, equal contiguous shares of the (class, 8-pattern tile) units
+    int grid = (int)std::min<long long>((p.nunits + MT - 1) / MT, (long long)c->nsm);
+    const char* genv = getenv("PB200_GRID");
+    if (genv && atoi(genv) > 0) grid = atoi(genv);
+    if (grid < 1) grid = 1;
+    kfn<<<grid, 384, smem, c->stream>>>(p);
+    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune_ps_kernel<%d,%s> grid %d x 384 threads, %zu B smem, %d D + %d x %d G slots", MT,
+             in_const ? "true" : "false", grid, smem, c->planps.nD, c->ps_banks, c->planps.nG);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int launch_prune_ps(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
+{
+    return c->ps_mt == 8 ? launch_prune_ps_t<8>(c, nclass, semantics, d_pi) : launch_prune_ps_t<4>(c, nclass, semantics, d_pi);
 }
 
 // ---- TMA-staged pruning kernel ----
@@ -876,7 +963,8 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
     const auto& L = c->last;
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], c->stream));
     if (launch_pt(c, c->n, L.kind, L.nr, L.set_stride, (const double*)(ds + L.off_sets), L.nmat, (const int*)(ds + L.off_set),
-                  (const double*)(ds + L.off_t), (double*)c->d_P.p, c->pstride, c->nuc4 ? PT_MODE_NUC4 : PT_MODE_AUTO, c->nnode, c->ns, c->NT, c->KS, c->ncodes))
+                  (const double*)(ds + L.off_t), (double*)c->d_P.p, c->pstride, c->nuc4 ? PT_MODE_NUC4 : PT_MODE_AUTO, c->nnode, c->ns, c->NT, c->KS, c->ncodes,
+                  c->ps_mt ? 1 : 0))
         return 1;
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], c->stream));
     {
@@ -886,7 +974,8 @@ static int run_kernels(pb200_ctx* c, cudaEvent_t* ev)
         // its warps move through the matrix ring together, so tip phases and DMMA phases do not overlap).
         const bool use_l1 = kenv ? strcmp(kenv, "tma") != 0 : true;
         c->fused_last = false;
-        if (c->nuc4v2) { if (launch_prune4v2(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
+        if (c->ps_mt) { if (launch_prune_ps(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
+        else if (c->nuc4v2) { if (launch_prune4v2(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
         else if (c->nuc4) { if (launch_prune4(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))) return 1; }
         else if (use_l1 ? launch_prune(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi))
                    : launch_prune_tma(c, L.nclass, L.semantics, (const double*)(ds + L.off_pi)))
@@ -954,7 +1043,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
     char* hs = (char*)c->h_stage;
     memcpy(hs + off_freq, freqK, (size_t)nclass * 8);
     for (int ph = 0; ph < NP; ph++) {                      // physical column order (kernels.cuh: phys_to_logical)
-        int j = c->nuc4 ? ph : phys_to_logical(ph);        // the 4-state kernel keeps the logical order
+        int j = (c->nuc4 || c->ps_mt) ? ph : phys_to_logical(ph);   // the 4-state and the P-stationary kernels keep the logical order
         ((double*)(hs + off_pi))[ph] = (j < n) ? pi[j] : 0.0;
     }
     if (set_stride > 0) memcpy(hs + off_sets, set_data, (size_t)nset * set_stride * 8);

@@ -158,6 +158,122 @@ std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* s
     return "";
 }
 
+// Programs of the P-stationary kernel (see plan.h): post-order with Sethi-Ullman child order; the tips of a node become a gather op
+// (emitted right before the node's own contraction op, so its product is alive as briefly as possible), the internal children a
+// contraction op.  G slots are handed out least-recently-released first, which lets the gather warps run ahead of the consumers.
+std::string plan_tree_ps(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                         const unsigned char* scale_flags, PlanPS& out)
+{
+    {
+        std::string e = check_tree(nnode, ns, root, nson, sons, maxsons);
+        if (!e.empty()) return e;
+    }
+    out = PlanPS();
+    std::vector<int> scale_idx(nnode, -1);
+    if (scale_flags)
+        for (int i = 0, k = 0; i < nnode; i++)
+            if (scale_flags[i] && i != root && i >= ns) { scale_idx[i] = k++; out.nscale = k; }
+    // D slots a subtree needs while it is computed, including the one its result occupies (0 for a node with tips only)
+    std::vector<int> need(nnode, 0), order;
+    {
+        std::vector<std::pair<int, int>> st;
+        st.push_back({root, 0});
+        while (!st.empty()) {
+            int v = st.back().first, k = st.back().second;
+            if (k < nson[v]) {
+                st.back().second++;
+                int c = sons[v * maxsons + k];
+                if (nson[c] > 0) st.push_back({c, 0});
+            }
+            else { order.push_back(v); st.pop_back(); }
+        }
+        for (int v : order) {
+            std::vector<int> cn;
+            for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] > 0) cn.push_back(need[c]); }
+            if (cn.empty()) { need[v] = 0; continue; }
+            std::sort(cn.begin(), cn.end(), std::greater<int>());
+            int held = 0, nd = 0;                           // results of the children finished so far that sit in D slots
+            for (size_t i = 0; i < cn.size(); i++) { nd = std::max(nd, cn[i] + held); if (cn[i] > 0) held++; }
+            need[v] = std::max(nd, held + 1);               // all children's results + the node's own
+        }
+    }
+    std::vector<char> d_used;
+    auto d_alloc = [&]() { for (size_t i = 0; i < d_used.size(); i++) if (!d_used[i]) { d_used[i] = 1; return (int)i; }
+                           d_used.push_back(1); return (int)d_used.size() - 1; };
+    std::vector<int> g_free, g_writes;                       // free list in release order; writes per chunk of each G slot
+    auto g_alloc = [&]() { if (g_free.empty()) { g_writes.push_back(0); return (int)g_writes.size() - 1; }
+                           int s = g_free.front(); g_free.erase(g_free.begin()); return s; };
+    struct Res { int kind = -1, slot = -1, k = 0; };
+    std::vector<Res> res(nnode);
+    std::vector<int> gops, dops;
+    struct Frame { int v; std::vector<int> ic; size_t next; };
+    std::vector<Frame> st;
+    auto push = [&](int v) {
+        Frame f; f.v = v; f.next = 0;
+        for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] > 0) f.ic.push_back(c); }
+        std::stable_sort(f.ic.begin(), f.ic.end(), [&](int a, int b) { return need[a] > need[b]; });
+        st.push_back(std::move(f));
+    };
+    push(root);
+    while (!st.empty()) {
+        Frame& f = st.back();
+        if (f.next < f.ic.size()) { int c = f.ic[f.next++]; push(c); continue; }
+        const int v = f.v;
+        std::vector<int> tips;
+        for (int j = 0; j < nson[v]; j++) { int c = sons[v * maxsons + j]; if (nson[c] == 0) tips.push_back(c); }
+        int gs = -1, gk = 0;
+        if (!tips.empty()) {
+            gs = g_alloc(); gk = g_writes[gs]++;
+            gops.push_back(gs); gops.push_back(gk); gops.push_back((int)tips.size()); gops.push_back(v);
+            for (int t : tips) gops.push_back(t);
+            out.n_gops++; out.ntip += (int)tips.size();
+        }
+        if (f.ic.empty() && v != root) {
+            if (scale_idx[v] >= 0) return "plan_tree_ps: a scaling node whose children are all tips";
+            res[v].kind = PS_G; res[v].slot = gs; res[v].k = gk;
+        }
+        else {
+            const int out_slot = (v == root) ? -1 : d_alloc();
+            // one step per internal child (a lone PS_NONE step for a root with tips only); what happens when the op is complete
+            // travels in its last step
+            const int nst = std::max<int>(1, (int)f.ic.size());
+            for (int i = 0; i < nst; i++) {
+                const bool has = i < (int)f.ic.size();
+                const int c = has ? f.ic[i] : -1;
+                int st[PS_STEP_INTS] = {0, 0, 0, 0, 0, 0, 0, 0};
+                st[0] = (has ? res[c].kind : PS_NONE) | (i == 0 ? PS_STEP_FIRST : 0) | (i == nst - 1 ? PS_STEP_LAST : 0);
+                st[1] = has ? res[c].slot : 0;
+                st[2] = has ? c : 0;
+                st[3] = has ? res[c].k : 0;
+                st[4] = out_slot; st[5] = scale_idx[v]; st[6] = gs; st[7] = gk;
+                dops.insert(dops.end(), st, st + PS_STEP_INTS);
+                if (has) out.n_internal_children++;
+            }
+            for (int c : f.ic) { if (res[c].kind == PS_D) d_used[res[c].slot] = 0; else g_free.push_back(res[c].slot); }
+            if (gs >= 0) g_free.push_back(gs);
+            res[v].kind = PS_D; res[v].slot = out_slot; res[v].k = 0;
+            out.n_dops += std::max<int>(1, (int)f.ic.size());
+        }
+        st.pop_back();
+    }
+    out.nD = (int)d_used.size();
+    out.nG = (int)g_writes.size();
+    out.prog.assign(PS_HDR, 0);
+    out.prog[0] = out.n_gops; out.prog[1] = out.n_dops; out.prog[2] = out.nG; out.prog[3] = out.nD;
+    out.prog.insert(out.prog.end(), g_writes.begin(), g_writes.end());
+    out.prog[4] = (int)out.prog.size();
+    out.prog.insert(out.prog.end(), gops.begin(), gops.end());
+    out.prog[5] = (int)out.prog.size();
+    // the kernel needs W_s next to every use of a G slot: fold it into the upper half of the k fields
+    for (size_t i = 0; i + PS_STEP_INTS <= dops.size(); i += PS_STEP_INTS) {
+        if ((dops[i] & PS_KIND_MASK) == PS_G) dops[i + 3] |= g_writes[dops[i + 1]] << 16;
+        if (dops[i + 6] >= 0) dops[i + 7] |= g_writes[dops[i + 6]] << 16;
+    }
+    out.prog.insert(out.prog.end(), dops.begin(), dops.end());
+    out.prog[6] = out.nscale;
+    return "";
+}
+
 // Macro-op program of the 4-state kernel (see plan.h).  Same Sethi-Ullman ordering as above; what is parked is
 // always the running product of the PARENT (the child's vector already multiplied by its branch matrix), so one
 // slot per pending node is enough and the kernel's register state is a single vector per pattern.

@@ -51,6 +51,30 @@ struct Plan4 {
 std::string plan_tree4(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
                        const unsigned char* scale_flags, Plan4& out);
 
+// ---- programs of the P-stationary kernel (prune_ps.cuh) ----
+// The kernel is warp-specialised: GATHER warps turn the tip children of a node into one vector per pattern (the product of the tips'
+// P(t) rows) in a shared-memory "G slot"; CONTRACTION warps do the internal children on the tensor path and keep their results in
+// "D slots".  Both walk the tree in the same post-order (Sethi-Ullman child order), each through its own op list:
+//   prog = [n_gops, n_steps, nG, nD, off_gops, off_steps, nscale, 0] [W_s: writes per chunk of G slot s] gops... steps...
+//   gop  = {gslot, k, ntip, node} + ntip tip node ids            -- the k-th write of the chunk into G slot gslot
+//   step = one internal child of a node, 8 ints: {kind (PS_D / PS_G / PS_NONE) | PS_STEP_FIRST | PS_STEP_LAST, slot, child node
+//          (selects the P(t) tile), k | W_slot << 16 (G slots: which write of the chunk), out (D slot of the node, -1 = root), scale_idx,
+//          tp_slot (G slot with the node's tip product, -1 = none), tp_k | W_tp << 16}; the last four describe the node and are used by its
+//          LAST step.  Fixed-size records: the kernel copies the table to shared memory and never chases a program counter.
+// A node with tips only is a gop alone: its G slot IS the node's vector (kind PS_G in the parent's step).  A root with tips only
+// gets one PS_NONE step.  The contraction warps hand a G slot back as soon as they have read it; the planner re-uses a G slot only
+// after the step that read it, in program order, so the full / empty handshake of the kernel cannot deadlock.  The output D slot of
+// a node never aliases one of its children.
+enum { PS_HDR = 8, PS_GOP_HDR = 4, PS_STEP_INTS = 8 };
+enum { PS_D = 0, PS_G = 1, PS_NONE = 2, PS_KIND_MASK = 3, PS_STEP_FIRST = 4, PS_STEP_LAST = 8 };
+struct PlanPS {
+    std::vector<int> prog;
+    int n_gops = 0, n_dops = 0 /* steps */, nG = 0, nD = 0, nscale = 0, ntip = 0;
+    long long n_internal_children = 0;
+};
+std::string plan_tree_ps(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
+                         const unsigned char* scale_flags, PlanPS& out);
+
 // Returns "" on success, else an error message.
 std::string plan_tree(int nnode, int ns, int root, const int* nson, const int* sons, int maxsons,
                       const unsigned char* scale_flags, Plan& out);

@@ -15,20 +15,21 @@ def _ptr(a, ct):
     return None if a is None else a.ctypes.data_as(C.POINTER(ct))
 
 
-def plan_tree(nnode, ns, root, nson, sons, scale_flags=None):
-    """Host-side planner only (no GPU): returns (program int32 array, nslots)."""
+def plan_tree(nnode, ns, root, nson, sons, scale_flags=None, ps=False):
+    """Host-side planner only (no GPU): returns (program int32 array, nslots).  ps: the P-stationary kernel's program."""
     L = lib()
+    fn = L.pb200_plan_tree_ps if ps else L.pb200_plan_tree
     nson = np.ascontiguousarray(nson, np.int32)
     sons = np.ascontiguousarray(sons, np.int32)
     maxsons = sons.shape[1]
     flags = None if scale_flags is None else np.ascontiguousarray(scale_flags, np.uint8)
     nslots = C.c_int(0)
-    need = L.pb200_plan_tree(C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
+    need = fn(C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
                              C.c_int(maxsons), _ptr(flags, C.c_ubyte), None, C.c_int(0), C.byref(nslots))
     if need < 0:
         raise PB200Error(L.pb200_last_error().decode())
     prog = np.zeros(need, np.int32)
-    L.pb200_plan_tree(C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
+    fn(C.c_int(nnode), C.c_int(ns), C.c_int(root), _ptr(nson, C.c_int), _ptr(sons, C.c_int),
                       C.c_int(maxsons), _ptr(flags, C.c_ubyte), _ptr(prog, C.c_int), C.c_int(need), C.byref(nslots))
     return prog, nslots.value
 

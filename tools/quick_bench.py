@@ -25,3 +25,4 @@ print("%s env[%s] npatt %d K %d: step %.4f ms  pt %.4f  prune %.4f  mix %.4f  ->
     which, " ".join("%s=%s" % (k, v_) for k, v_ in os.environ.items() if k.startswith("PB200_")), p.npatt, p.nclass,
     r["step"].mean(), r["pt"].mean(), r["prune"].mean(), r["mix"].mean(), upd / (r["step"].mean() * 1e-3),
     upd / (r["prune"].mean() * 1e-3), v))
+print("   ", tl.last_kernel())

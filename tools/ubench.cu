@@ -69,6 +69,43 @@ __global__ void dmma_stream(const double2* __restrict__ gB, double* out, int ite
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// P-stationary formulation: the P slab of a warp (one m-tile of 8 output states x 64 input states = 16 A fragments) stays in
+// registers, the child vectors of a chunk of 64 patterns are streamed from shared memory as B fragments (one LDS.64 per DMMA,
+// row stride 68 doubles), 8 accumulators (n-tiles) per warp.  MT2: two m-tiles per warp (each B fragment feeds two DMMAs).
+template <int MT>
+__global__ void dmma_pstat(double* out, int iters)
+{
+    extern __shared__ double sV[];      // [64 patterns][68]
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    for (int e = threadIdx.x; e < 64 * 68; e += blockDim.x) sV[e] = 1e-3 * (e % 7);
+    __syncthreads();
+    double a[MT][16], c[MT][8][2];
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) a[m][k] = 1.0 + 1e-9 * (k + lane + m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { c[m][i][0] = i; c[m][i][1] = lane; }
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ks++) {
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const double b = sV[(8 * nt + g) * 68 + 4 * ks + q];
+#pragma unroll
+                for (int m = 0; m < MT; m++) dmma884(c[m][nt][0], c[m][nt][1], a[m][ks], b);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += c[m][i][0] + c[m][i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __constant__ double cM[7680];
 __constant__ int cIdx[1024];
 
@@ -222,6 +259,28 @@ int main()
                 printf("  %d CTAs/SM x %2d warps: B by LDG %6.2f | by LDS %6.2f | in registers %6.2f\n", bps, threads / 32, flop / ms[0] / 1e9,
                        flop / ms[1] / 1e9, flop / ms[2] / 1e9);
             }
+    }
+    {
+        cudaFuncSetAttribute(dmma_pstat<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 68 * 8);
+        cudaFuncSetAttribute(dmma_pstat<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 68 * 8);
+        printf("== P-stationary stream (A = P slab in registers, B = child vectors by LDS.64 from a 64-pattern chunk), TFLOP/s\n");
+        for (int mt : {1, 2})
+            for (int bps : {1, 2})
+                for (int threads : {128, 256}) {
+                    const int iters = 400;
+                    double flop = (double)nsm * bps * (threads / 32) * iters * 128.0 * mt * 512.0;
+                    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                    float best = 1e30f;
+                    for (int r = 0; r < 4; r++) {
+                        cudaEventRecord(e0);
+                        if (mt == 1) dmma_pstat<1><<<nsm * bps, threads, 64 * 68 * 8>>>(out, iters);
+                        else dmma_pstat<2><<<nsm * bps, threads, 64 * 68 * 8>>>(out, iters);
+                        cudaEventRecord(e1); cudaEventSynchronize(e1);
+                        float t; cudaEventElapsedTime(&t, e0, e1);
+                        if (r && t < best) best = t;
+                    }
+                    printf("  %d m-tile(s) per warp, %d CTAs/SM x %d warps: %6.2f\n", mt, bps, threads / 32, flop / best / 1e9);
+                }
     }
     return 0;
     // constant matrices
