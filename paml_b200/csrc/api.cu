@@ -425,12 +425,13 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
         int mt = 0, banks = 0;
         if (err.empty()) {
             const size_t cap = (size_t)227 * 1024;
-            const int mt_try[4] = {8, 4, 8, 4}, bk_try[4] = {2, 2, 1, 1};
-            for (int i = 0; i < 4 && !mt; i++) {
-                if (menv && atoi(menv) != mt_try[i]) continue;
-                const size_t need = mt_try[i] == 8 ? PsCfg<8>::smem_bytes(ps.nD, ps.nG, bk_try[i], ps.ntip, ps.n_dops) : PsCfg<4>::smem_bytes(ps.nD, ps.nG, bk_try[i], ps.ntip, ps.n_dops);
-                if (need <= cap) { mt = mt_try[i]; banks = bk_try[i]; }
-            }
+            // two CTAs per SM: each gets half of the shared memory
+            const size_t half = (size_t)113 * 1024;
+            (void)cap; (void)menv;
+            for (int bk = 2; bk >= 1 && !mt; bk--)
+                if (PsCfg<4>::smem_bytes(ps.nD, ps.nG, bk, ps.ntip, ps.n_dops) <= half) { mt = 4; banks = bk; }
+            for (int bk = 2; bk >= 1 && !mt; bk--)
+                if (PsCfg<4>::smem_bytes(ps.nD, ps.nG, bk, ps.ntip, ps.n_dops) <= cap) { mt = 4; banks = bk; }
         }
         const bool want = kenv ? strcmp(kenv, "ps") == 0 : false;
         if (want && mt) {
@@ -628,21 +629,24 @@ static int launch_prune_ps_t(pb200_ctx* c, int nclass, int semantics, const doub
     p.semantics = semantics; p.nscale = c->planps.nscale;
     p.nbanks = c->ps_banks; p.ntip = c->planps.ntip;
     p.pi = d_pi; p.fhK = (double*)c->d_fhK.p;
-    // one CTA per SM, equal contiguous shares of the (class, 8-pattern tile) units
-    int grid = (int)std::min<long long>((p.nunits + MT - 1) / MT, (long long)c->nsm);
+    // equal contiguous shares of the (class, 8-pattern tile) units
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PS_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = (int)std::min<long long>((p.nunits + MT - 1) / MT, (long long)c->nsm * per_sm);
     const char* genv = getenv("PB200_GRID");
     if (genv && atoi(genv) > 0) grid = atoi(genv);
     if (grid < 1) grid = 1;
-    kfn<<<grid, 384, smem, c->stream>>>(p);
-    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune_ps_kernel<%d,%s> grid %d x 384 threads, %zu B smem, %d D + %d x %d G slots", MT,
-             in_const ? "true" : "false", grid, smem, c->planps.nD, c->ps_banks, c->planps.nG);
+    kfn<<<grid, PS_THREADS, smem, c->stream>>>(p);
+    snprintf(c->last_kernel, sizeof(c->last_kernel), "prune_ps_kernel<%d,%s> grid %d x %d threads, %zu B smem, %d per SM, %d D + %d x %d G slots", MT,
+             in_const ? "true" : "false", grid, (int)PS_THREADS, smem, per_sm, c->planps.nD, c->ps_banks, c->planps.nG);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 static int launch_prune_ps(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
 {
-    return c->ps_mt == 8 ? launch_prune_ps_t<8>(c, nclass, semantics, d_pi) : launch_prune_ps_t<4>(c, nclass, semantics, d_pi);
+    return launch_prune_ps_t<4>(c, nclass, semantics, d_pi);
 }
 
 // ---- TMA-staged pruning kernel ----

@@ -156,3 +156,109 @@ def run_program4(ops, tip_order, nslots, p, pmat_fn):
         lnf = np.log(np.maximum((p.freqK[:, None] * fhK).sum(0), 1e-300))
     lnf = np.where(p.fpatt > 0, lnf, 0.0)
     return -(lnf * p.fpatt).sum(), lnf
+
+
+# ---- programs of the P-stationary kernel (paml_b200/csrc/plan.h, PlanPS) ----
+PS_HDR, PS_GOP_HDR, PS_STEP_INTS = 8, 4, 8
+PS_D, PS_G, PS_NONE, PS_KIND_MASK, PS_STEP_FIRST, PS_STEP_LAST = 0, 1, 2, 3, 4, 8
+
+
+def run_program_ps(prog, p, pmat_fn):
+    """Interprets the gather-op list and the step table the way the kernel's two kinds of warps do: the gather ops in their order
+    fill G slots, the steps in their order consume them.  Checks what the full / empty handshake relies on: a G slot is only
+    rewritten after the step that read it (in program order), the k fields count the writes of a chunk, and a node's output D slot
+    never aliases one of its children."""
+    n, N, K = p.n, p.npatt, p.nclass
+    nscale = int(p.scale_flags.sum()) if p.scale_flags is not None else 0
+    n_gops, n_steps, nG, nD, off_g, off_s = (int(x) for x in prog[:6])
+    W = [int(x) for x in prog[PS_HDR:PS_HDR + nG]]
+    fhK = np.zeros((K, N))
+
+    def tip_rows(cls, tip):
+        P = pmat_fn(cls, tip)
+        zs = p.z[tip]
+        out = np.zeros((N, n))
+        for code in np.unique(zs):
+            states = p.charamap[code, :p.nchara[code]]
+            out[zs == code] = P[:, states].sum(1)
+        return out
+
+    for cls in range(K):
+        # the gather warps may run ahead as far as the slots allow; interleave lazily: run gather ops until the slot a step needs is full
+        g = [None] * nG
+        writes = [0] * nG
+        d = [None] * nD
+        state = {"pc": off_g, "done": 0}
+
+        def gather_until(slot, k):
+            while g[slot] is None or g[slot][0] != k:
+                assert state["done"] < n_gops, "step waits for a G slot no gather op fills"
+                pc = state["pc"]
+                gs, gk, nt, _node = (int(x) for x in prog[pc:pc + PS_GOP_HDR])
+                assert g[gs] is None, "gather op overwrites a G slot that has not been read"
+                assert gk == writes[gs], "k field does not count the writes of the chunk"
+                v = np.ones((N, n))
+                for t in prog[pc + PS_GOP_HDR:pc + PS_GOP_HDR + nt]:
+                    v = v * tip_rows(cls, int(t))
+                g[gs] = (gk, v)
+                writes[gs] += 1
+                state["pc"] = pc + PS_GOP_HDR + nt
+                state["done"] += 1
+
+        lnsc = np.zeros(N)
+        acc = None
+        children_d = []
+        for s in range(n_steps):
+            st = [int(x) for x in prog[off_s + s * PS_STEP_INTS: off_s + (s + 1) * PS_STEP_INTS]]
+            kind = st[0] & PS_KIND_MASK
+            if st[0] & PS_STEP_FIRST:
+                acc, children_d = None, []
+            if kind != PS_NONE:
+                if kind == PS_G:
+                    assert (st[3] >> 16) == W[st[1]]
+                    gather_until(st[1], st[3] & 0xffff)
+                    v = g[st[1]][1]
+                    g[st[1]] = None
+                else:
+                    assert d[st[1]] is not None, "read of an empty D slot"
+                    v = d[st[1]]
+                    children_d.append(st[1])
+                c = v @ pmat_fn(cls, st[2]).T
+                acc = c if acc is None else acc * c
+            if not (st[0] & PS_STEP_LAST):
+                continue
+            out_slot, sidx, tp, tpk = st[4], st[5], st[6], st[7]
+            if tp >= 0:
+                assert (tpk >> 16) == W[tp]
+                gather_until(tp, tpk & 0xffff)
+                acc = g[tp][1] if acc is None else acc * g[tp][1]
+                g[tp] = None
+            if sidx >= 0:
+                mx = acc.max(1)
+                tiny = mx < 1e-300
+                acc = acc.copy()
+                acc[tiny] = 1.0
+                acc[~tiny] /= mx[~tiny, None]
+                lnsc += np.where(tiny, -800.0, np.log(np.where(tiny, 1.0, mx)))
+            if out_slot >= 0:
+                assert out_slot not in children_d and d[out_slot] is None, "output D slot aliases a live slot"
+                d[out_slot] = acc
+                for c in children_d:
+                    d[c] = None
+            else:
+                fh = acc @ p.pi
+                if p.semantics == 0:
+                    fhK[cls] = np.log(np.where(fh <= 0, 1e-80, fh)) + lnsc
+                else:
+                    fh = np.where(fh <= 0, 1e-300, fh)
+                    fhK[cls] = np.log(fh) + lnsc if nscale else fh
+        assert state["done"] == n_gops and writes == W
+    if p.semantics == 0:
+        lnf = fhK[0]
+    elif nscale:
+        t = fhK.max(0)
+        lnf = t + np.log((p.freqK[:, None] * np.exp(fhK - t)).sum(0))
+    else:
+        lnf = np.log(np.maximum((p.freqK[:, None] * fhK).sum(0), 1e-300))
+    lnf = np.where(p.fpatt > 0, lnf, 0.0)
+    return -(lnf * p.fpatt).sum(), lnf

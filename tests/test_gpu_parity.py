@@ -202,3 +202,54 @@ def test_errors_are_loud(tl):
     bad = p.branch_set.copy(); bad[0, 0] = 5
     with pytest.raises(PB200Error):
         tl.eval(p.semantics, p.freqK, p.set_kind, p.nr, p.set_data, bad, p.branch_t, p.pi)
+
+
+# ---- the P-stationary, warp-specialised kernel (csrc/prune_ps.cuh; PB200_KERNEL=ps, read when the tree is set) ----
+@pytest.fixture()
+def tl_ps(monkeypatch):
+    monkeypatch.setenv("PB200_KERNEL", "ps")
+    t = TreeLikelihood(0)
+    yield t
+    t.close()
+
+
+@pytest.mark.parametrize("path", [g for g in GOLDEN if any(k in g for k in ("lysozyme", "mhc"))], ids=lambda g: g.split("/")[-1])
+def test_ps_kernel_on_codon_fixtures(tl_ps, path):
+    p = load_fixture(path)
+    tl_ps.set_problem(p)
+    v = tl_ps.eval_problem(p)
+    assert abs(v - p.ref_neg_lnL) <= REL_LNL * abs(p.ref_neg_lnL), (v, p.ref_neg_lnL)
+    np.testing.assert_allclose(tl_ps.lnf(), p.ref_lnf, rtol=0, atol=ABS_LNF)
+    if p.ref_fhK is not None:
+        _check_fhK(tl_ps.fhK(), p.ref_fhK, p.nscale > 0)
+    assert tl_ps.eval_problem(p) == v
+
+
+@pytest.mark.parametrize("npatt", [1, 9, 31, 32, 33, 255, 4097, 20011])
+def test_ps_kernel_ragged_sizes(tl_ps, npatt):
+    p = simulate.codon_m0_problem(npatt=max(npatt, 64), seed=5)
+    p.z = p.z[:, :npatt].copy(); p.fpatt = p.fpatt[:npatt].copy(); p.npatt = npatt
+    _check_against_oracle(tl_ps, p) if npatt < 5000 else None
+    if npatt >= 5000:
+        tl_ps.set_problem(p)
+        v = tl_ps.eval_problem(p)
+        assert "prune_ps_kernel" in tl_ps.last_kernel()
+        ref = TreeLikelihood(0)
+        try:
+            import os
+            os.environ["PB200_KERNEL"] = "warp"
+            ref.set_problem(p)
+            os.environ["PB200_KERNEL"] = "ps"
+            assert abs(ref.eval_problem(p) - v) <= 1e-12 * abs(v)
+            np.testing.assert_allclose(tl_ps.lnf(), ref.lnf(), rtol=0, atol=1e-10)
+        finally:
+            ref.close()
+
+
+def test_ps_kernel_classes_scaling_ambiguity(tl_ps):
+    _check_against_oracle(tl_ps, simulate.codon_sites_problem(ns=16, npatt=700, seed=3))
+    p = simulate.codon_m0_problem(ns=40, npatt=300, seed=9)
+    assert p.nscale > 0
+    _check_against_oracle(tl_ps, p)
+    _check_against_oracle(tl_ps, simulate.add_ambiguity(simulate.codon_m0_problem(ns=10, npatt=500, seed=6), 0.05))
+    assert "prune_ps_kernel" in tl_ps.last_kernel()

@@ -120,3 +120,45 @@ def test_default_scale_flags_match_reference():
         k, flags = likelihood.default_scale_flags(p.nnode, p.root, p.nson, p.sons, every)
         assert k == p.nscale
         np.testing.assert_array_equal(flags, p.scale_flags)
+
+
+@pytest.mark.parametrize("path", [g for g in GOLDEN if any(k in g for k in ("lysozyme_m0", "lysozyme_m2a", "mhc_m0", "lysozyme_freeratio"))],
+                         ids=lambda g: g.split("/")[-1])
+def test_program_ps_reproduces_reference(path):
+    # the P-stationary kernel's gather-op list + step table (codon fixtures incl. the 192-taxon MHC tree with scaling nodes)
+    from simprog import run_program_ps
+    p = load_fixture(path)
+    try:
+        prog, _ = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags, ps=True)
+    except likelihood.PB200Error as e:
+        assert "scaling node whose children are all tips" in str(e)
+        return
+    v, lnf = run_program_ps(prog, p, _pmat_fn(p))
+    assert abs(v - p.ref_neg_lnL) <= 1e-10 * abs(p.ref_neg_lnL)
+    np.testing.assert_allclose(lnf, p.ref_lnf, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape,ns", [("random", 40), ("balanced", 64), ("caterpillar", 30), ("random", 5), ("star", 6)])
+def test_program_ps_on_synthetic_trees(shape, ns):
+    from paml_b200.tree import random_tree
+    from simprog import run_program_ps
+    p = simulate.nuc_gtr_gamma_problem(ns=ns, npatt=200, seed=21 + ns, K=2)
+    if shape == "star":
+        nnode = ns + 1
+        p.nson = np.zeros(nnode, np.int32); p.nson[ns] = ns
+        p.sons = np.zeros((nnode, ns), np.int32); p.sons[ns, :] = np.arange(ns)
+        p.father = np.full(nnode, ns, np.int32); p.father[ns] = -1
+        p.root, p.nnode, p.maxsons = ns, nnode, ns
+        branch = np.linspace(0.05, 0.4, nnode)
+        p.nscale, p.scale_flags = 0, np.zeros(nnode, np.uint8)
+    else:
+        t = random_tree(ns, 7 + ns, shape=shape)
+        p.father, p.nson, p.sons, p.root, p.nnode, p.maxsons = t.father, t.nson, t.sons, t.root, t.nnode, t.maxsons
+        branch = t.branch
+        p.nscale, p.scale_flags = likelihood.default_scale_flags(t.nnode, t.root, t.nson, t.sons, 7)
+    p.branch_t = np.array([1.0, 0.4])[:, None] * branch[None, :]
+    p.branch_set = np.zeros((2, p.nnode), np.int32)
+    prog, _ = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags, ps=True)
+    r = oracle.lnl(p)
+    v, lnf = run_program_ps(prog, p, _pmat_fn(p))
+    assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
