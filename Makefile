@@ -16,7 +16,7 @@ all: $(LIB) oracle host
 # The drop-in programs: the unmodified reference driver (compiled from REF, nothing copied) + our lfun/lfundG.
 # Built only where the reference tree exists; the binaries travel to the GPU box like the .so files do.
 ifneq ($(wildcard $(REF)/codeml.c),)
-host: $(BIN)/codeml_b200 $(BIN)/baseml_b200
+host: $(BIN)/codeml_b200 $(BIN)/baseml_b200 $(BIN)/mcmctree_b200
 else
 host:
 	@echo "host: reference sources not present at $(REF); using prebuilt $(BIN) if any"
@@ -29,6 +29,9 @@ $(BIN)/codeml_b200: $(HOST)/codeml_b200.c $(HOST)/wrap_b200.inc $(HOST)/plfun_b2
 	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/codeml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
 $(BIN)/baseml_b200: $(HOST)/baseml_b200.c $(HOST)/wrap_b200.inc $(HOST)/plfun_b200.inc $(HOST)/pb200_gather.inc include/paml_b200.h $(BIN)/tools.o $(LIB)
 	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/baseml_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
+# mcmctree with its exact sequence likelihood (usedata = 1) through the same C ABI (host/mcmctree_b200.c)
+$(BIN)/mcmctree_b200: $(HOST)/mcmctree_b200.c include/paml_b200.h $(BIN)/tools.o $(LIB)
+	$(CC) -O3 -w -I$(REF) -I$(HOST) -Iinclude -o $@ $(HOST)/mcmctree_b200.c $(BIN)/tools.o -Lpaml_b200 -lpaml_b200 -Wl,-rpath,'$$ORIGIN/..' -lm
 
 $(LIB): $(CSRC)/api.cu $(CSRC)/kernels.cuh $(CSRC)/patterns.cpp $(CSRC)/plan.cpp $(CSRC)/plan.h $(CSRC)/prune4.cuh $(CSRC)/prune4v2.cuh $(CSRC)/prune_tma.cuh $(CSRC)/prune_ps.cuh $(CSRC)/cond_dmma.cuh $(CSRC)/eigen.cuh $(CSRC)/cond.cuh include/paml_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/api.cu $(CSRC)/plan.cpp $(CSRC)/patterns.cpp -ldl 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
