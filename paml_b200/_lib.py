@@ -14,7 +14,7 @@ SYMBOLS = [
     "pb200_create", "pb200_destroy", "pb200_last_error", "pb200_version", "pb200_set_data", "pb200_set_tree",
     "pb200_default_scale_flags", "pb200_eval", "pb200_eval_begin", "pb200_eval_end", "pb200_get_lnf", "pb200_get_fhK", "pb200_pmat",
     "pb200_nccl_unique_id", "pb200_comm_init", "pb200_p2p_local_handle", "pb200_p2p_init", "pb200_p2p_enable", "pb200_set_timing", "pb200_last_timing", "pb200_launch_count", "pb200_last_kernel",
-    "pb200_plan_tree", "pb200_plan_tree4", "pb200_measure_fp64_peak", "pb200_flush_l2", "pb200_bench_resident", "pb200_bench_e2e", "pb200_debug_set_program",
+    "pb200_plan_tree", "pb200_plan_tree_ps", "pb200_plan_tree4", "pb200_measure_fp64_peak", "pb200_flush_l2", "pb200_bench_resident", "pb200_bench_e2e", "pb200_debug_set_program",
     "pb200_compress_patterns", "pb200_eigen_qrev", "pb200_cond_update", "pb200_branch_lnl", "pb200_branch_newton", "pb200_cond_get",
 ]
 

@@ -345,6 +345,8 @@ long long pb200_launch_count(pb200_ctx *c) { return c ? c->launches : -1; }
 const char *pb200_last_kernel(pb200_ctx *c) { return "mock (CPU oracle, tests only)"; }
 int pb200_plan_tree(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons, const unsigned char *scale_flags, int *prog, int cap, int *nslots)
 { (void)nnode; (void)ns; (void)root; (void)nson; (void)sons; (void)maxsons; (void)scale_flags; (void)prog; (void)cap; (void)nslots; return -1; }
+int pb200_plan_tree_ps(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons, const unsigned char *scale_flags, int *prog, int cap, int *nslots)
+{ (void)nnode; (void)ns; (void)root; (void)nson; (void)sons; (void)maxsons; (void)scale_flags; (void)prog; (void)cap; (void)nslots; return -1; }
 int pb200_plan_tree4(int nnode, int ns, int root, const int *nson, const int *sons, int maxsons, const unsigned char *scale_flags, int *ops, int cap_ops,
                      int *tip_order, int cap_tips, int *ntip_out, int *nslots)
 { (void)nnode; (void)ns; (void)root; (void)nson; (void)sons; (void)maxsons; (void)scale_flags; (void)ops; (void)cap_ops; (void)tip_order; (void)cap_tips; (void)ntip_out; (void)nslots; return -1; }
