@@ -30,7 +30,7 @@ struct CondDmmaParams {
 };
 
 template <int NT, int KS>
-__global__ void __launch_bounds__(128, 3) cond_node_dmma_kernel(const CondDmmaParams p)
+__global__ void __launch_bounds__(128, 4) cond_node_dmma_kernel(const CondDmmaParams p)
 {
     constexpr int NP = 8 * NT, NTP = (NT + 1) / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
@@ -43,25 +43,6 @@ __global__ void __launch_bounds__(128, 3) cond_node_dmma_kernel(const CondDmmaPa
         const long long h = (item - (long long)cls * p.ntiles) * 8 + g;
         const long long hc = h < N ? h : N - 1;                 // dead rows walk a valid pattern, nothing is written
         double acc[NT][2];
-        // the vectors of the first two internal sons are requested together, before anything is computed: one HBM round trip per
-        // item instead of one per son (further sons of a multifurcation are loaded when their turn comes)
-        double apre[2][KS];
-        int npre = 0;
-        for (int s = 0; s < p.nson && npre < 2; s++) {
-            const int son = __ldg(p.sons + s);
-            if (son < p.ns) continue;
-            const double* src = p.cond + (((size_t)cls * nint + (son - p.ns)) * N + hc) * n;
-            if (npre == 0) {
-#pragma unroll
-                for (int ks = 0; ks < KS; ks++) { const int k = 4 * ks + q; apre[0][ks] = (k < n) ? __ldg(src + k) : 0.0; }
-            }
-            else {
-#pragma unroll
-                for (int ks = 0; ks < KS; ks++) { const int k = 4 * ks + q; apre[1][ks] = (k < n) ? __ldg(src + k) : 0.0; }
-            }
-            npre++;
-        }
-        int iint = 0;
         for (int s = 0; s < p.nson; s++) {
             const int son = __ldg(p.sons + s);
             const double* Pm = p.P + ((size_t)cls * p.nnode + son) * p.pstride;
@@ -73,21 +54,10 @@ __global__ void __launch_bounds__(128, 3) cond_node_dmma_kernel(const CondDmmaPa
                 for (int nt = 0; nt < NT; nt++) { const double2 v = __ldg(row + nt * 4 + q); t[nt][0] = v.x; t[nt][1] = v.y; }
             }
             else {                                              // internal son: src/codeml.c:3568-3575 on DMMA
+                const double* src = p.cond + (((size_t)cls * nint + (son - p.ns)) * N + hc) * n;
                 double a[KS];
-                if (iint == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < KS; ks++) a[ks] = apre[0][ks];
-                }
-                else if (iint == 1) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++) a[ks] = apre[1][ks];
-                }
-                else {
-                    const double* src = p.cond + (((size_t)cls * nint + (son - p.ns)) * N + hc) * n;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++) { const int k = 4 * ks + q; a[ks] = (k < n) ? __ldg(src + k) : 0.0; }
-                }
-                iint++;
+                for (int ks = 0; ks < KS; ks++) { const int k = 4 * ks + q; a[ks] = (k < n) ? __ldg(src + k) : 0.0; }
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++) t[nt][0] = t[nt][1] = 0.0;
                 const double2* B = reinterpret_cast<const double2*>(Pm) + lane;
