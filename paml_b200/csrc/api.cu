@@ -153,6 +153,9 @@ struct pb200_ctx {
     bool cond_dmma = false;     // the resident-vector kernels run on the DMMA path (n > 4; PB200_COND_DMMA=0 keeps the FP64-vector kernels)
     struct { int kind, nr, nset; long long set_stride; size_t off_sets; bool ok; } csets = {0, 0, 0, 0, 0, false};
     DevBuf d_eig;               // pb200_eigen_qrev: Q | pi | sets | info
+    DevBuf d_eig_warm;          // ... the previous solutions' eigenvectors, one slot per job (warm start of the Jacobi iteration)
+    int eig_warm_jobs = 0, eig_warm_n = 0;
+    unsigned long long eig_calls = 0;
     void* h_eig = nullptr;      // its pinned mirror
     size_t h_eig_cap = 0;
     bool fused_last = false;    // the last pruning launch already produced lnf and the sum
@@ -233,7 +236,7 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
                       &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs,
-                      &c->d_ops4, &c->d_tip_order, &c->d_zw, &c->d_eig,
+                      &c->d_ops4, &c->d_tip_order, &c->d_zw, &c->d_eig, &c->d_eig_warm, &c->d_prog_ps,
                       &c->d_cond, &c->d_cscale, &c->d_cstage, &c->d_cP, &c->d_cP3, &c->d_cpart, &c->d_cres, &c->d_cbr};
     for (DevBuf* b : bufs) b->release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1312,6 +1315,23 @@ extern "C" int pb200_eigen_qrev(pb200_ctx* c, int n, int njob, const double* Q, 
     EigenParams p;
     p.n = n; p.Q = (const double*)(ds + off_q); p.pi = (const double*)(ds + off_pi); p.sets = (double*)(ds + off_sets);
     p.set_stride = (long long)stride; p.info = (int*)(ds + off_info); p.max_sweeps = 40;
+    {
+        // Warm start: job j starts from the eigenvectors job j of the previous call ended with (the callers keep the job order:
+        // site class / branch type / branch).  Every 32nd call of a context starts cold again, so that the orthogonality of a basis
+        // handed down through thousands of optimiser steps cannot drift.  PB200_EIGEN_WARM=0 switches it off.
+        static int warm_on = -1;
+        if (warm_on < 0) { const char* e = getenv("PB200_EIGEN_WARM"); warm_on = !(e && atoi(e) == 0); }
+        p.warm = nullptr; p.use_warm = 0;
+        if (warm_on) {
+            if (njob > c->eig_warm_jobs || n != c->eig_warm_n) {
+                if (c->d_eig_warm.ensure((size_t)njob * EIG_WARM_DOUBLES * sizeof(double))) return 1;
+                CUDA_TRY(cudaMemsetAsync(c->d_eig_warm.p, 0, (size_t)njob * EIG_WARM_DOUBLES * sizeof(double), c->stream));
+                c->eig_warm_jobs = njob; c->eig_warm_n = n;
+            }
+            p.warm = (double*)c->d_eig_warm.p;
+            p.use_warm = (c->eig_calls++ % 32) != 0;
+        }
+    }
     const int m = n + (n & 1);
     const size_t smem = (size_t)3 * m * (m + 1) * sizeof(double);
     static bool attr_set[64] = {false};

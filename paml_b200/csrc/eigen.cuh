@@ -27,7 +27,13 @@ struct EigenParams {
     long long set_stride;
     int* info;               // [njob] sweeps used (negative: not converged)
     int max_sweeps;
+    // Warm start (optional): the eigenvectors of job j's PREVIOUS solution, [njob][EIG_WARM_DOUBLES] = {tag, V column-major m x (m+1)}.
+    // use_warm: start the iteration from them (A' = R0^T A R0 is then nearly diagonal when the matrix changed little -- the optimiser
+    // perturbs one parameter at a time -- and two sweeps instead of seven or eight suffice); the final vectors are always stored back.
+    double* warm;
+    int use_warm;
 };
+constexpr int EIG_WARM_DOUBLES = 8 + 64 * 65;
 
 constexpr int EIG_THREADS = 1024;
 constexpr int EIG_MAXM = 64;
@@ -77,6 +83,32 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
     }
     __syncthreads();
 
+    double* wbuf = p.warm ? p.warm + (size_t)job * EIG_WARM_DOUBLES : nullptr;
+    // the tag of a stored basis: dimension of the reduced problem and of the alphabet (a basis of another shape is ignored)
+    const double tag = (double)(nnew * 1024 + n);
+    if (wbuf && p.use_warm && wbuf[0] == tag && m >= 2) {
+        // V = R0;  T = A R0 (into A1);  A' = R0^T T (into A0, then copied to A1).  Jacobi then works on A' and keeps rotating V = R0 J1 J2 ...
+        const double* R0 = wbuf + 8;
+        for (int e = tid; e < m * LD; e += EIG_THREADS) V[e] = R0[e];
+        __syncthreads();
+        for (int e = tid; e < m * m; e += EIG_THREADS) {
+            const int i = e / m, k = e - i * m;
+            double t = 0.0;
+            for (int j = 0; j < m; j++) t = fma(A0[i * LD + j], V[k * LD + j], t);
+            A1[i * LD + k] = t;
+        }
+        __syncthreads();
+        for (int e = tid; e < m * m; e += EIG_THREADS) {
+            const int k = e / m, l = e - k * m;
+            double t = 0.0;
+            for (int i = 0; i < m; i++) t = fma(V[k * LD + i], A1[i * LD + l], t);
+            A0[k * LD + l] = t;
+        }
+        __syncthreads();
+        for (int e = tid; e < m * m; e += EIG_THREADS) { const int i = e / m, j = e - i * m; A1[i * LD + j] = A0[i * LD + j]; }
+        __syncthreads();
+    }
+
     const int bi = tid >> 5, bj = tid & 31;
     const bool upper = (bi <= bj) && (bj < half);
     const int nplayers = m - 1;
@@ -107,6 +139,11 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
     int sweeps = 0;
     bool converged = (m < 2) || frob2 == 0.0;
     bool last = false;                       // the sweep that starts below the quadratic-convergence threshold is the last
+    if (!converged && wbuf && p.use_warm && wbuf[0] == tag) {
+        // a warm start may already be within the quadratic-convergence threshold: then ONE sweep reaches the rounding floor
+        const double off0 = sumsq(A0, false);
+        if (off0 <= 1e-18 * frob2) last = true;
+    }
     double* Ac = A0;
     double* An = A1;
     while (!converged && sweeps < p.max_sweeps) {
@@ -183,6 +220,10 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eigen_qrev_kernel(const EigenP
         else if (off2 <= 1e-18 * frob2) last = true;
     }
 
+    if (wbuf) {                               // this solution's vectors are the next one's starting basis
+        for (int e = tid; e < m * LD; e += EIG_THREADS) wbuf[8 + e] = V[e];
+        if (tid == 0) wbuf[0] = converged ? tag : 0.0;
+    }
     // eigenvalues in decreasing order (ties: by index), like EigenSort
     if (tid < nnew) {
         const double d = Ac[tid * LD + tid];

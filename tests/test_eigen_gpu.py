@@ -126,3 +126,43 @@ def test_timing_report(tl):
         dn = (time.perf_counter() - t0) / (20 if njob == 1 else 2)
         print("\neigen n=%d njob=%d: device %.3f ms per call (%.3f ms per matrix, %d sweeps); numpy eigh on the host %.3f ms"
               % (n, njob, dt * 1e3, dt * 1e3 / njob, sw[0], dn * 1e3))
+
+
+def test_warm_start_follows_the_optimiser(tl):
+    """The Jacobi iteration starts from the eigenvectors of the previous call's solution (job for job): ming2 perturbs one
+    parameter at a time, so the next matrix is a small perturbation of the last one and two sweeps (one, for a finite-difference
+    step) replace seven or eight.  The result must not depend on where the iteration started: every solution of a 200-step chain of
+    perturbed matrices is checked like a cold one (U V = I, Q = U diag(Root) V, spectrum against numpy), i.e. the basis handed down
+    from call to call does not drift (every 32nd call starts cold)."""
+    rng = np.random.default_rng(11)
+    n = 61
+    S = rng.random((n, n)); S = S + S.T
+    pi = rng.random(n) + 0.05; pi /= pi.sum()
+
+    def make(S):
+        Q = S * pi[None, :]
+        np.fill_diagonal(Q, 0); np.fill_diagonal(Q, -Q.sum(1))
+        return Q
+
+    R, U, V, sw = tl.eigen_qrev(make(S), pi)
+    warm_sweeps, t_warm = [], 0.0
+    for step in range(200):
+        rel = 1e-7 if step % 3 else 3e-2                # finite-difference steps and line-search steps
+        S = S * (1 + rel * rng.standard_normal((n, n)))
+        S = (S + S.T) / 2
+        Q = make(S)
+        t0 = time.perf_counter()
+        R, U, V, sw = tl.eigen_qrev(Q, pi)
+        t_warm += time.perf_counter() - t0
+        assert sw[0] > 0
+        warm_sweeps.append(int(sw[0]))
+        _check(Q, pi, R[0], U[0], V[0])
+        if step % 20 == 0:
+            Rn, Un, Vn = models.eigen_reversible(Q, pi)
+            np.testing.assert_allclose(np.sort(R[0]), np.sort(Rn), rtol=0, atol=1e-12 * np.abs(Rn).max())
+            np.testing.assert_allclose(_pt(R[0], U[0], V[0], 0.3), _pt(Rn, Un, Vn, 0.3), rtol=0, atol=1e-13)
+    ws = np.array(warm_sweeps)
+    small = np.array([s for i, s in enumerate(warm_sweeps) if i % 3 and (i + 1) % 32])
+    print("\nwarm-started eigen_qrev, n = 61: %.3f ms per call on average; sweeps: median %d, after a 1e-7 perturbation %.2f on average, max %d"
+          % (t_warm / 200 * 1e3, np.median(ws), small.mean(), ws.max()))
+    assert small.mean() <= 2.5, small
