@@ -602,6 +602,24 @@ def main():
         if rank == 0:
             blocks[cfg] = b
 
+    if rank == 0 and world == 1:
+        # the opt-in P-stationary, warp-specialised kernel (csrc/prune_ps.cuh) on the headline workload, beside the default kernel
+        try:
+            os.environ["PB200_KERNEL"] = "ps"
+            alt = TreeLikelihood(local)
+            alt.set_problem(p)                       # PB200_KERNEL is read when the tree is set
+            os.environ.pop("PB200_KERNEL")
+            va = alt.eval_problem(p)
+            alt.bench_resident(3, FLUSH)
+            ra = alt.bench_resident(args.steps, FLUSH)
+            ach = algorithmic_flops(p) / (float(ra["prune"].mean()) * 1e-3) / 1e12
+            line["variants"] = dict(prune_ps_kernel=dict(kernel=alt.last_kernel(), prune_ms=float(ra["prune"].mean()), ms_per_step=float(ra["step"].mean()),
+                                                         roofline_frac=ach / fp64[0], neg_lnL_rel_diff_to_default=abs(va - m["neg_lnL"]) / abs(m["neg_lnL"]),
+                                                         note="PB200_KERNEL=ps; parity-green, not the default (see DESIGN.md section 4)"))
+            alt.close()
+        except Exception as exc:
+            os.environ.pop("PB200_KERNEL", None)
+            line["variants"] = dict(prune_ps_kernel=dict(failed=repr(exc)))
     if rank == 0:
         line["configs"] = blocks
         if want_cpu:

@@ -15,17 +15,26 @@
  *   - one context per locus (data and gene-tree topology are uploaded once; the topology never changes, only nodes[].branch);
  *   - JC69 / K80: PB200_KIND_K80 with {kappa};  F81 / F84 / HKY85: the spectral form eigenTN93 leaves in Root / Cijk at every
  *     UseLocus (src/mcmctree.c:932), PB200_KIND_CIJK -- P(t) agrees with PMatTN93 to rounding;
+ *   - the reference's bookkeeping around its own conditional vectors is switched off where it costs: UseLocus(locus, 1, ..) and
+ *     AcceptRejectLocus copy ALL conditional vectors of the locus between the two halves of com.conPin[] at every proposal
+ *     (src/mcmctree.c:911-912, 967-968: sG * 4 * npatt * (ns - 1) doubles -- 119 MB for 40 species x 19 000 patterns x 5 classes,
+ *     more than the whole GPU evaluation costs).  Nothing reads those vectors here, so the textually included program's memcpy
+ *     is a macro that skips copies INTO that buffer and is the C library's memcpy for everything else;
  *   - no node scaling (the reference has it commented out, src/mcmctree.c:937-944);
  *   - errors abort like zerror; there is no CPU fallback.
  * Environment: PB200_DEVICE = device ordinal (default 0); PB200_VERBOSE = 1 prints one line per upload. */
 #include <stdio.h>
+#include <string.h>
+static void *pbm_memcpy(void *dst, const void *src, size_t n);
 double lfun(double x[], int np);
 double lfundG(double x[], int np);
 #define lfun(a, b)   lfun_ref(a, b)
 #define lfundG(a, b) lfundG_ref(a, b)
+#define memcpy(d, s, n) pbm_memcpy(d, s, n)
 #include "mcmctree.c"
 #undef lfun
 #undef lfundG
+#undef memcpy
 #include "paml_b200.h"
 
 typedef struct {
@@ -37,6 +46,15 @@ typedef struct {
 } pbm_locus_t;
 static pbm_locus_t pbm_loci[NGENE];
 static long pbm_nupload = 0;
+
+static void *pbm_memcpy(void *dst, const void *src, size_t n)
+{
+   /* copies into the reference's own conditional-vector store (usedata = 1: com.conPin[0] .. + 2 com.sconP) are dead here */
+   if (mcmc.usedata == 1 && com.conPin[0] && com.sconP
+       && (char*)dst >= (char*)com.conPin[0] && (char*)dst < (char*)com.conPin[0] + 2 * com.sconP)
+      return dst;
+   return memcpy(dst, src, n);
+}
 
 static void pbm_die(const char *what)
 {
