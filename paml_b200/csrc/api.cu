@@ -83,6 +83,20 @@ static const void* g_const_owner[64] = {nullptr};
 static unsigned long long g_const_gen[64] = {0};
 // bumped whenever a device or pinned buffer of any context is re-allocated: captured evaluation graphs hold raw pointers
 static unsigned long long g_alloc_gen = 1;
+static void const_prog_forget(int device, const void* owner);
+// c_P4 (the 4-state kernel's matrices in constant memory) is re-filled by every launch that uses it: a context may only do so once
+// the launches of the context that used it before have finished
+static const void* g_p4_user[64] = {nullptr};
+static int claim_const_p4(int device, const void* ctx)
+{
+    if (device < 0 || device >= 64) return 0;
+    if (g_p4_user[device] && g_p4_user[device] != ctx) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return fail("cudaDeviceSynchronize failed: %s", cudaGetErrorString(e));
+    }
+    g_p4_user[device] = ctx;
+    return 0;
+}
 
 // launch parameters of one evaluation of the branch function (see prepare_branch)
 struct BranchLaunch {
@@ -164,6 +178,7 @@ struct pb200_ctx {
     bool fused_last = false;    // the last pruning launch already produced lnf and the sum
     // the program the last pruning launch wanted in c_prog (use_const_prog)
     const int* cp_data = nullptr; size_t cp_n = 0; unsigned long long cp_gen = 0;
+    int cp_base = 0, graph_cp_base = 0;      // where in c_prog it sits; where it sat when the evaluation graph was captured
     // One evaluation as a CUDA graph (H2D of the parameter block, P(t), pruning, mixture, D2H of the result): optimisers and MCMC
     // samplers call pb200_eval thousands of times with nothing changed but the numbers in the parameter block, and on small data
     // an evaluation is launch-bound.  The second evaluation with the same key is captured, later ones replay it.
@@ -251,7 +266,8 @@ extern "C" void pb200_destroy(pb200_ctx* c)
     if (c->eval_graph) cudaGraphDestroy(c->eval_graph);
     for (int r = 0; r < 64; r++) if (c->peer_map[r]) cudaIpcCloseMemHandle(c->peer_map[r]);
     if (c->xchg) cudaFree(c->xchg);
-    if (c->device < 64 && g_const_owner[c->device] == c) g_const_owner[c->device] = nullptr;
+    const_prog_forget(c->device, c);
+    if (c->device < 64 && g_p4_user[c->device] == c) g_p4_user[c->device] = nullptr;
     DevBuf* bufs[] = {&c->d_z, &c->d_fpatt, &c->d_amb_n, &c->d_amb_map, &c->d_amb_mask, &c->d_prog, &c->d_stage, &c->d_P, &c->d_fhK,
                       &c->d_lnf, &c->d_partial, &c->d_counter, &c->d_result, &c->d_flush, &c->d_item_partial, &c->d_peer_ptrs,
                       &c->d_ops4, &c->d_tip_order, &c->d_zw, &c->d_eig, &c->d_eig_warm, &c->d_prog_ps,
@@ -468,16 +484,52 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// c_prog holds ONE program per device: (re)load it when another context or another tree's program is in it, and remember what
-// this context's pruning launch wants there (an evaluation replayed as a graph re-establishes it before the launch).
+// c_prog (24 KB of constant memory per device) holds the pruning programs the kernels read on their critical path.  Programs of up to
+// PB200_CONST_SLOT_INTS ints -- trees up to a few hundred taxa -- get one of four slots, so that the contexts of a multi-gene model or
+// of mcmctree's loci, which take turns at every evaluation, keep their programs resident; a longer program takes the whole buffer.
+// A slot is handed to another context only after a device-wide synchronisation (its previous owner's kernels may still be reading
+// it).  The launch reads the offset from c->cp_base; an evaluation replayed as a graph re-establishes (and checks) it first.
+#define PB200_CONST_SLOTS 4
+#define PB200_CONST_SLOT_INTS (PB200_CONST_PROG_INTS / PB200_CONST_SLOTS)
+struct ConstSlot { const void* owner; unsigned long long gen, stamp; };
+static ConstSlot g_cslot[64][PB200_CONST_SLOTS];
+static unsigned long long g_cslot_clock = 0;
+static void const_prog_forget(int device, const void* owner)
+{
+    if (device < 0 || device >= 64) return;
+    for (int k = 0; k < PB200_CONST_SLOTS; k++) if (g_cslot[device][k].owner == owner) g_cslot[device][k].owner = nullptr;
+    if (g_const_owner[device] == owner) g_const_owner[device] = nullptr;
+}
 static int use_const_prog(pb200_ctx* c, const int* data, size_t n, unsigned long long gen)
 {
-    if (g_const_owner[c->device] != c || g_const_gen[c->device] != gen) {
-        if (g_const_owner[c->device] && g_const_owner[c->device] != c) CUDA_TRY(cudaDeviceSynchronize());   // another context may be using it
-        CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, data, n * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
-        g_const_owner[c->device] = c; g_const_gen[c->device] = gen;
-    }
+    const int dev = c->device;
     c->cp_data = data; c->cp_n = n; c->cp_gen = gen;
+    if (n > PB200_CONST_SLOT_INTS) {
+        // the whole buffer
+        if (g_const_owner[dev] != c || g_const_gen[dev] != gen) {
+            bool others = (g_const_owner[dev] && g_const_owner[dev] != c);
+            for (int k = 0; k < PB200_CONST_SLOTS; k++) { if (g_cslot[dev][k].owner && g_cslot[dev][k].owner != c) others = true; g_cslot[dev][k].owner = nullptr; }
+            if (others) CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, data, n * sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+            g_const_owner[dev] = c; g_const_gen[dev] = gen;
+        }
+        c->cp_base = 0;
+        return 0;
+    }
+    ConstSlot* S = g_cslot[dev];
+    int k = -1;
+    for (int i = 0; i < PB200_CONST_SLOTS; i++) if (S[i].owner == c) k = i;
+    if (k >= 0 && S[k].gen == gen && !g_const_owner[dev]) { S[k].stamp = ++g_cslot_clock; c->cp_base = k * PB200_CONST_SLOT_INTS; return 0; }
+    bool sync = false;
+    if (g_const_owner[dev]) { sync = (g_const_owner[dev] != c); g_const_owner[dev] = nullptr; for (int i = 0; i < PB200_CONST_SLOTS; i++) S[i].owner = nullptr; k = -1; }
+    if (k < 0) {
+        for (int i = 0; i < PB200_CONST_SLOTS && k < 0; i++) if (!S[i].owner) k = i;
+        if (k < 0) { k = 0; for (int i = 1; i < PB200_CONST_SLOTS; i++) if (S[i].stamp < S[k].stamp) k = i; sync = true; }   // least recently used
+    }
+    if (sync) CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_prog, data, n * sizeof(int), (size_t)k * PB200_CONST_SLOT_INTS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    S[k].owner = c; S[k].gen = gen; S[k].stamp = ++g_cslot_clock;
+    c->cp_base = k * PB200_CONST_SLOT_INTS;
     return 0;
 }
 
@@ -566,10 +618,10 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
         p.prefetch_b = penv ? atoi(penv) : 0;        // measured: explicit L1 prefetch of the next tiles costs more than it hides
     }
     p.prog = (const int*)c->d_prog.p;
-    p.prog_in_const = 0;
+    p.prog_in_const = 0; p.prog_base = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
         if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen)) return 1;
-        p.prog_in_const = 1;
+        p.prog_in_const = 1; p.prog_base = c->cp_base;
     }
     void (*kfn)(const PruneParams) = p.prog_in_const ? L.fn : L.fn_g;
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -637,11 +689,11 @@ template <int MT>
 static int launch_prune_ps_t(pb200_ctx* c, int nclass, int semantics, const double* d_pi)
 {
     PrunePsParams p;
-    p.prog = (const int*)c->d_prog_ps.p;
+    p.prog = (const int*)c->d_prog_ps.p; p.prog_base = 0;
     bool in_const = false;
     if (c->planps.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
         if (use_const_prog(c, c->planps.prog.data(), c->planps.prog.size(), c->plan_gen_ps)) return 1;
-        in_const = true;
+        in_const = true; p.prog_base = c->cp_base;
     }
     void (*kfn)(const PrunePsParams) = in_const ? prune_ps_kernel<MT, true> : prune_ps_kernel<MT, false>;
     const size_t smem = PsCfg<MT>::smem_bytes(c->planps.nD, c->planps.nG, c->ps_banks, c->planps.ntip, c->planps.n_dops);
@@ -726,10 +778,10 @@ static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const doubl
     PruneTmaParams pp;
     PruneParams& p = pp.base;
     p.prog = (const int*)c->d_prog.p;
-    p.prog_in_const = 0;
+    p.prog_in_const = 0; p.prog_base = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
         if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen)) return 1;
-        p.prog_in_const = 1;
+        p.prog_in_const = 1; p.prog_base = c->cp_base;
     }
     p.z = (const unsigned char*)c->d_z.p;
     p.zstride = c->zstride; p.npatt = c->npatt;
@@ -767,10 +819,10 @@ static int launch_prune4_t(pb200_ctx* c, int nclass, int semantics, const double
 {
     Prune4Params p;
     p.prog = (const int*)c->d_prog.p;
-    p.prog_in_const = 0;
+    p.prog_in_const = 0; p.prog_base = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
         if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen)) return 1;
-        p.prog_in_const = 1;
+        p.prog_in_const = 1; p.prog_base = c->cp_base;
     }
     p.z = (const unsigned char*)c->d_z.p; p.zstride = c->zstride; p.npatt = c->npatt;
     p.P = (const double*)c->d_P.p; p.pstride = (int)c->pstride; p.nnode = c->nnode; p.nclass = nclass; p.nslots = c->plan.nslots;
@@ -827,11 +879,11 @@ static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const doub
         c->zw_dirty = false;
     }
     Prune4v2Params p;
-    p.ops = (const int*)c->d_ops4.p; p.nops = (int)pl.ops.size() / 2;
+    p.ops = (const int*)c->d_ops4.p; p.nops = (int)pl.ops.size() / 2; p.prog_base = 0;
     bool in_const = false;
     if (pl.ops.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
         if (use_const_prog(c, pl.ops.data(), pl.ops.size(), c->plan_gen)) return 1;
-        in_const = true;
+        in_const = true; p.prog_base = c->cp_base;
     }
     p.zw = (const unsigned int*)c->d_zw.p; p.zwstride = c->zstride; p.npatt = c->npatt; p.ngroups = ngroups;
     p.P = (const double*)c->d_P.p; p.pstride = (int)c->pstride; p.nnode = c->nnode; p.nclass = nclass; p.nslots = pl.nslots;
@@ -859,6 +911,7 @@ static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const doub
         p.cp_class_stride = per_class; p.cp_base = -16 * c->ns;
         double* cp4 = nullptr;
         CUDA_TRY(cudaGetSymbolAddress((void**)&cp4, c_P4));
+        if (claim_const_p4(c->device, c)) return 1;         // (a no-op inside pb200_eval_begin, which has claimed it already)
         for (int c0 = 0; c0 < nclass; c0 += cls_per_launch) {
             const int ncl = std::min(cls_per_launch, nclass - c0);
             for (int k = 0; k < ncl; k++)            // stream-ordered: the previous launch has finished reading c_P4
@@ -1080,6 +1133,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
     c->last.semantics = semantics; c->last.nclass = nclass; c->last.kind = set_kind; c->last.nr = nr; c->last.nmat = nmat;
     c->last.mix_blocks = mix_blocks; c->last.set_stride = set_stride;
     c->last.off_freq = off_freq; c->last.off_pi = off_pi; c->last.off_sets = off_sets; c->last.off_t = off_t; c->last.off_set = off_set;
+    if (c->nuc4v2 && claim_const_p4(c->device, c)) return 1;      // before any capture: it may synchronise the device
     // ---- the evaluation as a graph (see pb200_ctx::eval_exec) ----
     if (c->graph_off < 0) { const char* e = getenv("PB200_EVAL_GRAPH"); c->graph_off = (e && atoi(e) == 0) ? 1 : 0; }
     const bool graph_ok = !c->graph_off && !c->timing && !c->comm && !c->p2p && c->nranks <= 1 && !c->zw_dirty;
@@ -1101,9 +1155,17 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
     if (graph_ok && c->eval_exec && same(key, c->gkey)) {
         // replay: only the numbers in the pinned parameter block have changed
         if (c->cp_data && use_const_prog(c, c->cp_data, c->cp_n, c->cp_gen)) return 1;
-        CUDA_TRY(cudaGraphLaunch(c->eval_exec, c->stream));
-        c->launches += c->graph_launches;
-        c->graph_replays++;
+        if (c->cp_base == c->graph_cp_base) {
+            CUDA_TRY(cudaGraphLaunch(c->eval_exec, c->stream));
+            c->launches += c->graph_launches;
+            c->graph_replays++;
+        }
+        else {
+            // the program moved to another slot of c_prog (more contexts than slots): the captured launches read the old one
+            cudaGraphExecDestroy(c->eval_exec); c->eval_exec = nullptr;
+            if (enqueue()) return 1;
+            c->gkey_seen = key;
+        }
     }
     else if (graph_ok && same(key, c->gkey_seen) && c->cp_data && !same(key, c->gkey_small)) {
         // the previous evaluation had the same shape and ran launch by launch (programs, packings and buffers are in place): capture
@@ -1125,7 +1187,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
             // 20 states) while the 4-state shape with its per-class launches and constant-memory copies does (81.9 -> 64.3 us).
             small = ok && nnodes < 8;
             if (ok && !small) ok = (cudaGraphInstantiate(&c->eval_exec, g, 0) == cudaSuccess);
-            if (ok && !small) { c->eval_graph = g; c->graph_launches = c->launches - l0; c->gkey = key; }
+            if (ok && !small) { c->eval_graph = g; c->graph_launches = c->launches - l0; c->gkey = key; c->graph_cp_base = c->cp_base; }
             else { if (g) cudaGraphDestroy(g); c->eval_exec = nullptr; cudaGetLastError(); c->launches = l0; }
         }
         if (ok && !small) { CUDA_TRY(cudaGraphLaunch(c->eval_exec, c->stream)); c->graph_replays++; }

@@ -267,6 +267,7 @@ __constant__ double c_P4[PB200_CONST_P4_DOUBLES];
 struct PruneParams {
     const int* prog;            // plan.h program in global memory (used when it does not fit c_prog)
     int prog_in_const;          // 1: read c_prog instead
+    int prog_base;              // ... from this offset (c_prog holds the programs of up to four contexts, see use_const_prog)
     const unsigned char* z;     // [ns][zstride] compact codes
     long long zstride, npatt, ntiles, nitems;
     const double* Pbuf;         // [nclass][nnode][pstride]
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
     // program words: constant memory (uniform loads) when the program fits there, else read-only global loads; an
     // explicit branch per access keeps the two address spaces apart (a selected pointer would turn generic)
     // (CP is a template parameter so that each instantiation holds exactly one kind of load)
-    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
+    auto PW = [&](int i) -> int { if (CP) return c_prog[p.prog_base + i]; else return __ldg(p.prog + i); };
     const int nops = PW(0), ntip = PW(2);
     const int ops0 = PW(3);
 

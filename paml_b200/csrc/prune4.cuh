@@ -15,6 +15,7 @@ namespace pb200 {
 struct Prune4Params {
     const int* prog;
     int prog_in_const;
+    int prog_base;              // offset of the program in c_prog
     const unsigned char* z;     // [ns][zstride] compact codes
     long long zstride, npatt;
     const double* P;            // [nclass][nnode][pstride]: internal branch P[j][k] row-major; tip branch PT[code][j]
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
     }
     // program words: constant memory (uniform loads) when the program fits there, else read-only global loads;
     // an explicit branch per access keeps the two address spaces apart (a selected pointer would become generic)
-    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
+    auto PW = [&](int i) -> int { if (CP) return c_prog[p.prog_base + i]; else return __ldg(p.prog + i); };
     const int nops = PW(0), ntip = PW(2);
     const int ops0 = PW(3);
     // per-warp ring of tip codes (cp.async, 4 bytes per lane): [slot][PPT][32], two halves of HALF4 tips; one half is

@@ -21,6 +21,7 @@ namespace pb200 {
 struct Prune4v2Params {
     const int* ops;             // macro-ops (2 ints each) in global memory; constant memory copy when ops_in_const
     int nops;
+    int prog_base;              // offset of the op words in c_prog
     const unsigned int* zw;     // [ngroups][zwstride] walk-ordered tip codes, 4 per word
     long long zwstride, npatt;
     int ngroups;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             if (PCONST) {
                 // the node index is re-read from the constant-memory op word with the (uniform) op counter, so that the
                 // compiler can see the address is warp-uniform and use the uniform datapath (LDCU -> UR operands of DFMA)
-                const int ci = (c_prog[2 * op + 1] & 0xffff) * 16 + p.cp_base + (int)blockIdx.y * p.cp_class_stride;
+                const int ci = (c_prog[p.prog_base + 2 * op + 1] & 0xffff) * 16 + p.cp_base + (int)blockIdx.y * p.cp_class_stride;
 #pragma unroll
                 for (int e = 0; e < 16; e++) Pr[e] = c_P4[ci + e];
             }
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune4v2_kernel(const Prune4v2P
             }
         };
         auto op_words = [&](int op, int& w0, int& w1) {
-            if (CP) { w0 = c_prog[2 * op]; w1 = c_prog[2 * op + 1]; }
+            if (CP) { w0 = c_prog[p.prog_base + 2 * op]; w1 = c_prog[p.prog_base + 2 * op + 1]; }
             else { const int2 w = __ldg(reinterpret_cast<const int2*>(p.ops) + op); w0 = w.x; w1 = w.y; }
         };
 

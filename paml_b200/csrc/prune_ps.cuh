@@ -22,6 +22,7 @@ namespace pb200 {
 
 struct PrunePsParams {
     const int* prog;            // plan.h PlanPS program in global memory (used when it does not fit c_prog)
+    int prog_base;              // offset of the program in c_prog
     const unsigned char* z;     // [ns][zstride] compact codes
     long long zstride, npatt;
     long long ntile;            // 8-pattern tiles per class
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) prune_ps_kernel(const PrunePsPa
     constexpr int CH = C::CH, STRIDE = C::STRIDE;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
+    auto PW = [&](int i) -> int { if (CP) return c_prog[p.prog_base + i]; else return __ldg(p.prog + i); };
     const int n_gops = PW(0), n_steps = PW(1), nG = PW(2), nD = PW(3), off_g = PW(4), off_d = PW(5);
     const int nGS = nG * p.nbanks;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smraw);      // [nGS]: gather warps -> contraction warps
