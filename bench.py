@@ -603,7 +603,7 @@ def main():
             blocks[cfg] = b
 
     if rank == 0 and world == 1:
-        # the opt-in P-stationary, warp-specialised kernel (csrc/prune_ps.cuh) on the headline workload, beside the default kernel
+        # the P-stationary, warp-specialised kernel (csrc/prune_ps.cuh; default for small alignments only) on the headline workload
         try:
             os.environ["PB200_KERNEL"] = "ps"
             alt = TreeLikelihood(local)
@@ -615,7 +615,7 @@ def main():
             ach = algorithmic_flops(p) / (float(ra["prune"].mean()) * 1e-3) / 1e12
             line["variants"] = dict(prune_ps_kernel=dict(kernel=alt.last_kernel(), prune_ms=float(ra["prune"].mean()), ms_per_step=float(ra["step"].mean()),
                                                          roofline_frac=ach / fp64[0], neg_lnL_rel_diff_to_default=abs(va - m["neg_lnL"]) / abs(m["neg_lnL"]),
-                                                         note="PB200_KERNEL=ps; parity-green, not the default (see DESIGN.md section 4)"))
+                                                         note="PB200_KERNEL=ps; the default only for small alignments, where it cuts latency (see DESIGN.md section 4)"))
             alt.close()
         except Exception as exc:
             os.environ.pop("PB200_KERNEL", None)

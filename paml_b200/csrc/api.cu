@@ -153,7 +153,9 @@ struct pb200_ctx {
     PlanPS planps;              // program of the P-stationary kernel (prune_ps.cuh; 61..64-state shape only)
     unsigned long long plan_gen_ps = 0;
     int ps_banks = 1;
-    int ps_mt = 0;              // > 0: evaluations run prune_ps_kernel<ps_mt> (P(t), tip rows and pi in LOGICAL state order)
+    int ps_mt = 0;              // > 0: THIS evaluation runs prune_ps_kernel<ps_mt> (P(t), tip rows and pi in LOGICAL state order)
+    int ps_avail_mt = 0;        // > 0: the tree has a P-stationary program (set by pb200_set_tree); which kernel runs is decided per evaluation
+    int ps_mode = 0;            // PB200_KERNEL as read by pb200_set_tree: 0 by size, 1 = ps always, 2 = never
     DevBuf d_prog_ps;
     DevBuf d_prog;
     // eval
@@ -342,7 +344,7 @@ extern "C" int pb200_set_data(pb200_ctx* c, int n, int ns, long long npatt, cons
         if (c->d_amb_mask.ensure(256)) return 1;
         CUDA_TRY(cudaMemcpy(c->d_amb_mask.p, mask.data(), 256, cudaMemcpyHostToDevice));
     }
-    if (ns != c->ns) { c->nnode = 0; c->root = -1; c->plan = Plan(); c->plan4 = Plan4(); c->planps = PlanPS(); c->ps_mt = 0; }   // the plan was built for another tip count: pb200_set_tree must follow
+    if (ns != c->ns) { c->nnode = 0; c->root = -1; c->plan = Plan(); c->plan4 = Plan4(); c->planps = PlanPS(); c->ps_mt = 0; c->ps_avail_mt = 0; }   // the plan was built for another tip count: pb200_set_tree must follow
     c->n = n; c->ns = ns; c->npatt = npatt; c->zstride = zstride; c->cleandata = cleandata; c->ncodes = ncodes;
     choose_shape(n, &c->NT, &c->KS);
     c->ld = 4 * c->KS;
@@ -451,31 +453,29 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
     static unsigned long long gen_counter = 0;
     c->cond_nclass = 0; c->csets.ok = false;               // resident conditional vectors belong to the previous topology
     c->plan = pl; c->nnode = nnode; c->root = root; c->plan_gen = ++gen_counter;
-    c->ps_mt = 0;
-    if (c->NT == 8 && c->KS == 16 && !c->nuc4) {
-        // P-stationary kernel: chunks of 64 patterns when two CTAs' slots fit an SM's shared memory, else 32
+    c->ps_mt = 0; c->ps_avail_mt = 0;
+    {
         const char* kenv = getenv("PB200_KERNEL");
-        const char* menv = getenv("PB200_PS_MT");
+        c->ps_mode = !kenv ? 0 : strcmp(kenv, "ps") == 0 ? 1 : 2;
+    }
+    if (c->NT == 8 && c->KS == 16 && !c->nuc4 && c->ps_mode != 2) {
+        // the P-stationary kernel's programs; two CTAs per SM when their slots fit half of the shared memory each (two banks of
+        // G slots preferred).  Whether an evaluation uses it is decided in pb200_eval_begin (choose_ps).
         PlanPS ps;
         err = plan_tree_ps(nnode, c->ns, root, nson, sons, maxsons, scale_flags, ps);    // fails for shapes the kernel does not cover
-        // chunks of 64 patterns when the slots fit an SM's shared memory (two banks of G slots preferred), else 32
         int mt = 0, banks = 0;
         if (err.empty()) {
-            const size_t cap = (size_t)227 * 1024;
-            // two CTAs per SM: each gets half of the shared memory
-            const size_t half = (size_t)113 * 1024;
-            (void)cap; (void)menv;
+            const size_t cap = (size_t)227 * 1024, half = (size_t)113 * 1024;
             for (int bk = 2; bk >= 1 && !mt; bk--)
                 if (PsCfg<4>::smem_bytes(ps.nD, ps.nG, bk, ps.ntip, ps.n_dops) <= half) { mt = 4; banks = bk; }
             for (int bk = 2; bk >= 1 && !mt; bk--)
                 if (PsCfg<4>::smem_bytes(ps.nD, ps.nG, bk, ps.ntip, ps.n_dops) <= cap) { mt = 4; banks = bk; }
         }
-        const bool want = kenv ? strcmp(kenv, "ps") == 0 : false;
-        if (want && mt) {
+        if (mt) {
             if (c->d_prog_ps.ensure(ps.prog.size() * sizeof(int))) return 1;
             CUDA_TRY(cudaMemcpyAsync(c->d_prog_ps.p, ps.prog.data(), ps.prog.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            c->planps = ps; c->plan_gen_ps = ++gen_counter; c->ps_mt = mt; c->ps_banks = banks;
+            c->planps = ps; c->plan_gen_ps = ++gen_counter; c->ps_avail_mt = mt; c->ps_banks = banks;
         }
     }
     c->have_eval = false;
@@ -711,7 +711,8 @@ static int launch_prune_ps_t(pb200_ctx* c, int nclass, int semantics, const doub
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PS_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    int grid = (int)std::min<long long>((p.nunits + MT - 1) / MT, (long long)c->nsm * per_sm);
+    // (little work: one 8-pattern tile per CTA rather than full chunks on a few SMs -- the walk of a chunk then costs a quarter)
+    int grid = (int)std::min<long long>(p.nunits, (long long)c->nsm * per_sm);
     const char* genv = getenv("PB200_GRID");
     if (genv && atoi(genv) > 0) grid = atoi(genv);
     if (grid < 1) grid = 1;
@@ -1103,6 +1104,16 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
     }
     CUDA_TRY(cudaSetDevice(c->device));
 
+    // Which pruning kernel (61..64 states)?  The P-stationary kernel splits the STATES of a tile over four warps, so the walk of one
+    // 8-pattern tile costs a quarter of what it costs the warp-independent kernel: with little work (every tile gets its own CTA) an
+    // evaluation is that walk's latency, and the P-stationary kernel wins (8 taxa x 130 patterns: 29.5 -> 18.7 us, 40 taxa x 300:
+    // 154 -> 95 us; tools/small_latency.py); with enough tiles to fill the SMs several times the warp-independent kernel's better
+    // overlap wins (10^4 patterns: 32.8 against 39.4 us).  Measured crossover: about four 8-pattern tiles per SM.
+    c->ps_mt = 0;
+    if (c->ps_avail_mt) {
+        const long long units = (long long)nclass * ((c->npatt + 7) / 8);
+        if (c->ps_mode == 1 || (c->ps_mode == 0 && units <= 4LL * c->nsm)) c->ps_mt = c->ps_avail_mt;
+    }
     // one pinned staging block -> one H2D copy: freqK | pi (padded) | sets | branch_t | branch_set
     size_t off_freq = 0;
     size_t off_pi = align16(off_freq + (size_t)nclass * 8);

@@ -134,6 +134,26 @@ class TreeLikelihood:
     def eval_problem(self, p):
         return self.eval(p.semantics, p.freqK, p.set_kind, p.nr, p.set_data, p.branch_set, p.branch_t, p.pi)
 
+    def eval_begin_problem(self, p):
+        """pb200_eval_begin: enqueue the evaluation and return without waiting (collect with eval_end)."""
+        freqK = np.ascontiguousarray(p.freqK, np.float64)
+        set_data = np.ascontiguousarray(p.set_data, np.float64)
+        if set_data.ndim == 1:
+            set_data = set_data.reshape(1, -1)
+        branch_set = np.ascontiguousarray(p.branch_set, np.int32)
+        branch_t = np.ascontiguousarray(p.branch_t, np.float64)
+        pi = np.ascontiguousarray(p.pi, np.float64)
+        check(self._L.pb200_eval_begin(self._ctx, C.c_int(p.semantics), C.c_int(freqK.shape[0]), _ptr(freqK, C.c_double),
+                                       C.c_int(p.set_kind), C.c_int(p.nr), C.c_int(set_data.shape[0]),
+                                       C.c_longlong(set_data.shape[1]), _ptr(set_data, C.c_double),
+                                       _ptr(branch_set, C.c_int), _ptr(branch_t, C.c_double), _ptr(pi, C.c_double)))
+        self.nclass = freqK.shape[0]
+
+    def eval_end(self):
+        out = C.c_double(0)
+        check(self._L.pb200_eval_end(self._ctx, C.byref(out)))
+        return out.value
+
     def lnf(self):
         out = np.zeros(self.npatt)
         check(self._L.pb200_get_lnf(self._ctx, _ptr(out, C.c_double)))

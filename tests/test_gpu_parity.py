@@ -253,3 +253,55 @@ def test_ps_kernel_classes_scaling_ambiguity(tl_ps):
     _check_against_oracle(tl_ps, p)
     _check_against_oracle(tl_ps, simulate.add_ambiguity(simulate.codon_m0_problem(ns=10, npatt=500, seed=6), 0.05))
     assert "prune_ps_kernel" in tl_ps.last_kernel()
+
+
+def test_program_in_global_memory(monkeypatch):
+    """Programs that do not fit the constant-memory buffer are read from global memory (the kernels' second instantiation):
+    forced here for every kernel family."""
+    monkeypatch.setenv("PB200_NO_CONST_PROG", "1")
+    t = TreeLikelihood(0)
+    try:
+        _check_against_oracle(t, simulate.codon_m0_problem(npatt=300, seed=5))
+        _check_against_oracle(t, simulate.nuc_gtr_gamma_problem(ns=30, npatt=900, seed=4, K=3))
+        _check_against_oracle(t, simulate.aa_gamma_problem(ns=12, npatt=300, seed=4))
+    finally:
+        t.close()
+    monkeypatch.setenv("PB200_KERNEL", "ps")
+    t = TreeLikelihood(0)
+    try:
+        _check_against_oracle(t, simulate.codon_sites_problem(ns=12, npatt=150, seed=3))
+        assert "prune_ps_kernel<4,false>" in t.last_kernel()
+    finally:
+        t.close()
+
+
+def test_many_contexts_take_turns():
+    """Six contexts on one device evaluated in turn, as the gene units of a partitioned model or mcmctree's loci are: more contexts
+    than constant-memory program slots (least-recently-used eviction), evaluation graphs captured per context and dropped when a
+    program changes slot, the shared constant matrix buffer of the 4-state kernel claimed in turn.  Every value is checked against
+    the oracle, and every context must return the same bits each round."""
+    from oracle import oracle
+    probs = [simulate.nuc_gtr_gamma_problem(ns=8 + 3 * i, npatt=400 + 50 * i, seed=40 + i, K=5) for i in range(4)]
+    probs += [simulate.codon_m0_problem(npatt=200, seed=8), simulate.aa_gamma_problem(ns=10, npatt=250, seed=9)]
+    ctxs = [TreeLikelihood(0) for _ in probs]
+    try:
+        ref = [oracle.lnl(p)["neg_lnL"] for p in probs]
+        for t, p in zip(ctxs, probs):
+            t.set_problem(p)
+        first = None
+        for rnd in range(6):
+            vals = [t.eval_problem(p) for t, p in zip(ctxs, probs)]
+            for v, r in zip(vals, ref):
+                assert abs(v - r) <= REL_LNL * abs(r), (rnd, v, r)
+            if first is None:
+                first = vals
+            assert vals == first, (rnd, vals, first)
+        # enqueued on all contexts before any is collected (one host thread driving several contexts, as the shim does)
+        for rnd in range(3):
+            for t, p in zip(ctxs, probs):
+                t.eval_begin_problem(p)
+            vals = [t.eval_end() for t in ctxs]
+            assert vals == first, (rnd, vals, first)
+    finally:
+        for t in ctxs:
+            t.close()
