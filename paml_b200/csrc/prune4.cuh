@@ -44,9 +44,10 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
     }
     // program words: constant memory (uniform loads) when the program fits there, else read-only global loads;
     // an explicit branch per access keeps the two address spaces apart (a selected pointer would become generic)
-    auto PW = [&](int i) -> int { if (CP) return c_prog[p.prog_base + i]; else return __ldg(p.prog + i); };
-    const int nops = PW(0), ntip = PW(2);
-    const int ops0 = PW(3);
+    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };      // absolute positions: see prune_kernel
+    const int cb = CP ? p.prog_base : 0, hdr0 = cb + PROG_HDR;
+    const int nops = PW(cb), ntip = PW(cb + 2);
+    const int ops0 = cb + PW(cb + 3);
     // per-warp ring of tip codes (cp.async, 4 bytes per lane): [slot][PPT][32], two halves of HALF4 tips; one half is
     // consumed (no synchronisation per tip) while the other is being refilled, one cp.async group per half
     constexpr int HALF4 = 8, RING4 = 2 * HALF4;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(THREADS) prune4_kernel(const Prune4Params p)
                     const int tipi = tip0 + i;
                     if (tipi < ntip) {
                         unsigned char* dst = ring + ((half * HALF4 + i) * PPT + u) * 32 + l4;
-                        if (hh + 4 <= p.zstride) cp_async4(dst, p.z + (size_t)PW(PROG_HDR + tipi) * p.zstride + hh);
+                        if (hh + 4 <= p.zstride) cp_async4(dst, p.z + (size_t)PW(hdr0 + tipi) * p.zstride + hh);
                         else *reinterpret_cast<unsigned int*>(dst) = 0u;      // past the padded row: dead patterns read state 0
                     }
                 }

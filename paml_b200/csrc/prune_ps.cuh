@@ -112,8 +112,9 @@ __global__ void __launch_bounds__(PS_THREADS, 2) prune_ps_kernel(const PrunePsPa
     constexpr int CH = C::CH, STRIDE = C::STRIDE;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    auto PW = [&](int i) -> int { if (CP) return c_prog[p.prog_base + i]; else return __ldg(p.prog + i); };
-    const int n_gops = PW(0), n_steps = PW(1), nG = PW(2), nD = PW(3), off_g = PW(4), off_d = PW(5);
+    auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };      // absolute positions: see prune_kernel
+    const int cb = CP ? p.prog_base : 0, whdr = cb + PS_HDR;
+    const int n_gops = PW(cb), n_steps = PW(cb + 1), nG = PW(cb + 2), nD = PW(cb + 3), off_g = cb + PW(cb + 4), off_d = cb + PW(cb + 5);
     const int nGS = nG * p.nbanks;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smraw);      // [nGS]: gather warps -> contraction warps
     unsigned long long* empty = full + nGS;                                         // [nGS]: contraction warps -> gather warps
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) prune_ps_kernel(const PrunePsPa
             for (int go = 0; go < n_gops; go++) {
                 const int gslot = PW(pcg), k = PW(pcg + 1), nt = PW(pcg + 2);
                 const int S = bank * nG + gslot;
-                const int nw = jt * PW(PS_HDR + gslot) + k;           // how many times this slot has been written before
+                const int nw = jt * PW(whdr + gslot) + k;           // how many times this slot has been written before
                 const int c0 = live ? cd[t * CH] : 0, c1 = (live && nt > 1) ? cd[(t + 1) * CH] : 0;
                 const double2* r0 = reinterpret_cast<const double2*>(Pcls + (size_t)PW(pcg + PS_GOP_HDR) * p.pstride + (size_t)c0 * 64) + jj;
                 double2 a[C::NPC];
