@@ -180,6 +180,7 @@ struct pb200_ctx {
     bool fused_last = false;    // the last pruning launch already produced lnf and the sum
     // the program the last pruning launch wanted in c_prog (use_const_prog)
     const int* cp_data = nullptr; size_t cp_n = 0; unsigned long long cp_gen = 0;
+    bool cp_slotted = false;
     int cp_base = 0, graph_cp_base = 0;      // where in c_prog it sits; where it sat when the evaluation graph was captured
     // One evaluation as a CUDA graph (H2D of the parameter block, P(t), pruning, mixture, D2H of the result): optimisers and MCMC
     // samplers call pb200_eval thousands of times with nothing changed but the numbers in the parameter block, and on small data
@@ -485,8 +486,10 @@ extern "C" int pb200_set_tree(pb200_ctx* c, int nnode, int root, const int* nson
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // c_prog (24 KB of constant memory per device) holds the pruning programs the kernels read on their critical path.  Programs of up to
-// PB200_CONST_SLOT_INTS ints -- trees up to a few hundred taxa -- get one of four slots, so that the contexts of a multi-gene model or
-// of mcmctree's loci, which take turns at every evaluation, keep their programs resident; a longer program takes the whole buffer.
+// PB200_CONST_SLOT_INTS ints -- trees up to a few hundred taxa -- of the kernels that take an offset (the 4-state macro-op kernel, the
+// P-stationary kernel: `slotted`) get one of four slots, so that the contexts of a multi-gene model or
+// of mcmctree's loci, which take turns at every evaluation, keep their programs resident; a longer program, and the warp-independent kernels' (their code is
+// measurably sensitive to the extra index arithmetic: +3.8 % on the 32-taxon shape), takes the whole buffer.
 // A slot is handed to another context only after a device-wide synchronisation (its previous owner's kernels may still be reading
 // it).  The launch reads the offset from c->cp_base; an evaluation replayed as a graph re-establishes (and checks) it first.
 #define PB200_CONST_SLOTS 4
@@ -500,11 +503,11 @@ static void const_prog_forget(int device, const void* owner)
     for (int k = 0; k < PB200_CONST_SLOTS; k++) if (g_cslot[device][k].owner == owner) g_cslot[device][k].owner = nullptr;
     if (g_const_owner[device] == owner) g_const_owner[device] = nullptr;
 }
-static int use_const_prog(pb200_ctx* c, const int* data, size_t n, unsigned long long gen)
+static int use_const_prog(pb200_ctx* c, const int* data, size_t n, unsigned long long gen, bool slotted)
 {
     const int dev = c->device;
-    c->cp_data = data; c->cp_n = n; c->cp_gen = gen;
-    if (n > PB200_CONST_SLOT_INTS) {
+    c->cp_data = data; c->cp_n = n; c->cp_gen = gen; c->cp_slotted = slotted;
+    if (n > PB200_CONST_SLOT_INTS || !slotted) {
         // the whole buffer
         if (g_const_owner[dev] != c || g_const_gen[dev] != gen) {
             bool others = (g_const_owner[dev] && g_const_owner[dev] != c);
@@ -618,10 +621,10 @@ static int launch_prune(pb200_ctx* c, int nclass, int semantics, const double* d
         p.prefetch_b = penv ? atoi(penv) : 0;        // measured: explicit L1 prefetch of the next tiles costs more than it hides
     }
     p.prog = (const int*)c->d_prog.p;
-    p.prog_in_const = 0; p.prog_base = 0;
+    p.prog_in_const = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
-        if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen)) return 1;
-        p.prog_in_const = 1; p.prog_base = c->cp_base;
+        if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen, false)) return 1;
+        p.prog_in_const = 1;
     }
     void (*kfn)(const PruneParams) = p.prog_in_const ? L.fn : L.fn_g;
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -692,7 +695,7 @@ static int launch_prune_ps_t(pb200_ctx* c, int nclass, int semantics, const doub
     p.prog = (const int*)c->d_prog_ps.p; p.prog_base = 0;
     bool in_const = false;
     if (c->planps.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
-        if (use_const_prog(c, c->planps.prog.data(), c->planps.prog.size(), c->plan_gen_ps)) return 1;
+        if (use_const_prog(c, c->planps.prog.data(), c->planps.prog.size(), c->plan_gen_ps, true)) return 1;
         in_const = true; p.prog_base = c->cp_base;
     }
     void (*kfn)(const PrunePsParams) = in_const ? prune_ps_kernel<MT, true> : prune_ps_kernel<MT, false>;
@@ -779,10 +782,10 @@ static int launch_prune_tma(pb200_ctx* c, int nclass, int semantics, const doubl
     PruneTmaParams pp;
     PruneParams& p = pp.base;
     p.prog = (const int*)c->d_prog.p;
-    p.prog_in_const = 0; p.prog_base = 0;
+    p.prog_in_const = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
-        if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen)) return 1;
-        p.prog_in_const = 1; p.prog_base = c->cp_base;
+        if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen, false)) return 1;
+        p.prog_in_const = 1;
     }
     p.z = (const unsigned char*)c->d_z.p;
     p.zstride = c->zstride; p.npatt = c->npatt;
@@ -822,8 +825,8 @@ static int launch_prune4_t(pb200_ctx* c, int nclass, int semantics, const double
     p.prog = (const int*)c->d_prog.p;
     p.prog_in_const = 0; p.prog_base = 0;
     if (c->plan.prog.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
-        if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen)) return 1;
-        p.prog_in_const = 1; p.prog_base = c->cp_base;
+        if (use_const_prog(c, c->plan.prog.data(), c->plan.prog.size(), c->plan_gen, false)) return 1;
+        p.prog_in_const = 1;
     }
     p.z = (const unsigned char*)c->d_z.p; p.zstride = c->zstride; p.npatt = c->npatt;
     p.P = (const double*)c->d_P.p; p.pstride = (int)c->pstride; p.nnode = c->nnode; p.nclass = nclass; p.nslots = c->plan.nslots;
@@ -883,7 +886,7 @@ static int launch_prune4v2_t(pb200_ctx* c, int nclass, int semantics, const doub
     p.ops = (const int*)c->d_ops4.p; p.nops = (int)pl.ops.size() / 2; p.prog_base = 0;
     bool in_const = false;
     if (pl.ops.size() <= PB200_CONST_PROG_INTS && c->device < 64 && !getenv("PB200_NO_CONST_PROG")) {
-        if (use_const_prog(c, pl.ops.data(), pl.ops.size(), c->plan_gen)) return 1;
+        if (use_const_prog(c, pl.ops.data(), pl.ops.size(), c->plan_gen, true)) return 1;
         in_const = true; p.prog_base = c->cp_base;
     }
     p.zw = (const unsigned int*)c->d_zw.p; p.zwstride = c->zstride; p.npatt = c->npatt; p.ngroups = ngroups;
@@ -1165,7 +1168,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
     };
     if (graph_ok && c->eval_exec && same(key, c->gkey)) {
         // replay: only the numbers in the pinned parameter block have changed
-        if (c->cp_data && use_const_prog(c, c->cp_data, c->cp_n, c->cp_gen)) return 1;
+        if (c->cp_data && use_const_prog(c, c->cp_data, c->cp_n, c->cp_gen, c->cp_slotted)) return 1;
         if (c->cp_base == c->graph_cp_base) {
             CUDA_TRY(cudaGraphLaunch(c->eval_exec, c->stream));
             c->launches += c->graph_launches;
@@ -1182,7 +1185,7 @@ extern "C" int pb200_eval_begin(pb200_ctx* c, int semantics, int nclass, const d
         // the previous evaluation had the same shape and ran launch by launch (programs, packings and buffers are in place): capture
         if (c->eval_exec) { cudaGraphExecDestroy(c->eval_exec); c->eval_exec = nullptr; }
         if (c->eval_graph) { cudaGraphDestroy(c->eval_graph); c->eval_graph = nullptr; }
-        if (use_const_prog(c, c->cp_data, c->cp_n, c->cp_gen)) return 1;
+        if (use_const_prog(c, c->cp_data, c->cp_n, c->cp_gen, c->cp_slotted)) return 1;
         const long long l0 = c->launches;
         bool small = false;
         bool ok = (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess);

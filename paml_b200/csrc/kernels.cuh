@@ -278,8 +278,7 @@ __constant__ double c_P4[PB200_CONST_P4_DOUBLES];
 
 struct PruneParams {
     const int* prog;            // plan.h program in global memory (used when it does not fit c_prog)
-    int prog_in_const;          // 1: read c_prog instead
-    int prog_base;              // ... from this offset (c_prog holds the programs of up to four contexts, see use_const_prog)
+    int prog_in_const;          // 1: read c_prog instead (this kernel's program always sits at the start of c_prog: use_const_prog)
     const unsigned char* z;     // [ns][zstride] compact codes
     long long zstride, npatt, ntiles, nitems;
     const double* Pbuf;         // [nclass][nnode][pstride]
@@ -399,11 +398,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
     // program words: constant memory (uniform loads) when the program fits there, else read-only global loads; an
     // explicit branch per access keeps the two address spaces apart (a selected pointer would turn generic)
     // (CP is a template parameter so that each instantiation holds exactly one kind of load)
-    // (indices are ABSOLUTE positions in c_prog: the slot offset is folded into `cb`, `hdr0` and `pc` once, not added at every read)
     auto PW = [&](int i) -> int { if (CP) return c_prog[i]; else return __ldg(p.prog + i); };
-    const int cb = CP ? p.prog_base : 0, hdr0 = cb + PROG_HDR;
-    const int nops = PW(cb), ntip = PW(cb + 2);
-    const int ops0 = cb + PW(cb + 3);
+    const int nops = PW(0), ntip = PW(2);
+    const int ops0 = PW(3);
 
     // Warps that share a sub-partition (same warp % 4) share one DMMA pipe.  Started together they stay in
     // lockstep -- all gathering tips at once, then all queueing on the tensor pipe -- and the phases simply add
@@ -437,7 +434,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
         // prologue of the tip-code ring: the first RING tips of the walk
 #pragma unroll
         for (int i = 0; i < C::RING; i++) {
-            if (i < ntip && lane < C::ROWS / 4) cp_async4(ring + i * C::ROWS + 4 * lane, zt + (size_t)PW(hdr0 + i) * p.zstride + 4 * lane);
+            if (i < ntip && lane < C::ROWS / 4) cp_async4(ring + i * C::ROWS + 4 * lane, zt + (size_t)PW(PROG_HDR + i) * p.zstride + 4 * lane);
             cp_async_commit();
         }
         int ti = 0;                                          // tips consumed so far
@@ -515,7 +512,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                 for (int k = 0; k < (two ? 2 : 1); k++) {   // refill the ring entries just consumed
                     const int nx = ti + k + C::RING;
                     if (nx < ntip && lane < C::ROWS / 4)
-                        cp_async4(ring + ((ti + k) % C::RING) * C::ROWS + 4 * lane, zt + (size_t)PW(hdr0 + nx) * p.zstride + 4 * lane);
+                        cp_async4(ring + ((ti + k) % C::RING) * C::ROWS + 4 * lane, zt + (size_t)PW(PROG_HDR + nx) * p.zstride + 4 * lane);
                     cp_async_commit();
                 }
                 ti += two ? 2 : 1;
@@ -577,7 +574,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_kernel(const PruneParams 
                     {
                         const int nx = ti + C::RING;
                         if (nx < ntip && lane < C::ROWS / 4)
-                            cp_async4(ring + (ti % C::RING) * C::ROWS + 4 * lane, zt + (size_t)PW(hdr0 + nx) * p.zstride + 4 * lane);
+                            cp_async4(ring + (ti % C::RING) * C::ROWS + 4 * lane, zt + (size_t)PW(PROG_HDR + nx) * p.zstride + 4 * lane);
                         cp_async_commit();
                     }
                     ti++;

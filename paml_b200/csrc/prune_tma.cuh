@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) prune_tma_kernel(const PruneTma
     unsigned char* ring = warp_base + (size_t)p.nslots * C::SLOT_DOUBLES * sizeof(double);
     const long long N = p.npatt;
 
-    const int* prog = p.prog_in_const ? c_prog + p.prog_base : p.prog;
+    const int* prog = p.prog_in_const ? c_prog : p.prog;
     const int nops = prog[0], ntip = prog[2], nmat = prog[4];
     const int* tip_order = prog + PROG_HDR;
     const int* matseq = prog + prog[5];
