@@ -14,6 +14,10 @@
 //     "G slot" (src/codeml.c:3555-3567), running ahead of the contraction warps: G slots are double-banked by chunk parity and
 //     handed over through full / empty mbarriers, tip codes are staged one chunk ahead with cp.async.
 // Everything is in LOGICAL state order (pt_kernel, logical = 1).  Programs: plan.h (PlanPS).
+// Use (pb200_eval_begin): splitting a tile's STATES over four warps makes the walk of one 8-pattern tile four times shorter than
+// prune_kernel's, so this kernel is the default when there is little work (small alignments: every tile gets its own CTA and an
+// evaluation is that walk's latency); with enough tiles to fill the SMs several times prune_kernel's sixteen independent warps per
+// SM overlap better and it is the default (profiles/r2_small_latency.txt).
 #pragma once
 #include "kernels.cuh"
 #include "prune_tma.cuh"     // mbarrier helpers
