@@ -51,6 +51,38 @@ SCENARIOS = {
 }
 
 
+# the reference's TipDate example with the exact likelihood (examples/TipDate.HIV2/mcmctree.ExactlnL.ctl): 33 dated HIV-2 sequences,
+# birth-death-sequential-sampling prior, strict clock, HKY85 + G5, ambiguity data -- the stock control file with a shorter chain
+CTL_TIPDATE = """          seed = 1357
+       seqfile = HIV2ge.txt
+      treefile = HIV2ge.tre
+       outfile = out
+      mcmcfile = mcmc.txt
+       seqtype = 0
+       usedata = 1
+         ndata = 1
+         clock = {clock}
+       TipDate = 1 100
+       RootAge = B(0.5, 2.0, 0.01, 0.01)
+         model = 4
+         alpha = 0.5
+         ncatG = 5
+     cleandata = 0
+       BDparas = 2 1 0 1.8 M
+   kappa_gamma = 6 2
+   alpha_gamma = 1 1
+   rgene_gamma = 2 10
+  sigma2_gamma = 1 1
+      finetune = 1: 0.5 1.2 .08 .05 .05 .05
+         print = 1
+        burnin = {burnin}
+      sampfreq = 2
+       nsample = {nsample}
+"""
+SCENARIOS["tipdate_hiv2_clock1"] = dict(ctl=CTL_TIPDATE, files=("HIV2ge.txt", "HIV2ge.tre"), clock=1)
+SCENARIOS["tipdate_hiv2_clock2"] = dict(ctl=CTL_TIPDATE, files=("HIV2ge.txt", "HIV2ge.tre"), clock=2)
+
+
 def _table(path):
     rows = open(path).read().split("\n")
     hdr = rows[0].split("\t")
@@ -63,9 +95,17 @@ def _scenario(exe, tmp_path, name, burnin=100, nsample=150):
     for tag, prog in (("new", exe), ("ref", REF)):
         d = tmp_path / tag
         d.mkdir()
-        for f in ("mtCDNApri123.txt", "mtCDNApri.trees"):
-            os.symlink(os.path.join(EX, f), d / f)
-        open(d / "mcmctree.ctl", "w").write(CTL.format(burnin=burnin, nsample=nsample, **SCENARIOS[name]))
+        sc = dict(SCENARIOS[name])
+        ctl = sc.pop("ctl", CTL)
+        for f in sc.pop("files", ("mtCDNApri123.txt", "mtCDNApri.trees")):
+            if f == "HIV2ge.tre":
+                # the shipped file holds five trees; this version of mcmctree accepts one: keep the first (the RAxML tree)
+                txt = open(os.path.join(EX, f)).read()
+                first = txt[txt.index("("):txt.index(";") + 1]
+                open(d / f, "w").write("33 1\n\n" + first + "\n")
+            else:
+                os.symlink(os.path.join(EX, f), d / f)
+        open(d / "mcmctree.ctl", "w").write(ctl.format(burnin=burnin, nsample=nsample, **sc))
         r = subprocess.run([prog, "mcmctree.ctl"], cwd=d, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                            text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:]
@@ -82,7 +122,8 @@ def _scenario(exe, tmp_path, name, burnin=100, nsample=150):
 def test_mcmctree_host_logic(mock_bin, tmp_path, name):  # noqa: F811
     if not os.path.exists(REF):
         pytest.skip("reference binary not built (make -C oracle ref)")
-    _scenario(os.path.join(mock_bin, "mcmctree_mock"), tmp_path, name, burnin=40, nsample=60)
+    big = name.startswith("tipdate")                    # 33 taxa x 1107 sites through the scalar oracle: keep the chain short
+    _scenario(os.path.join(mock_bin, "mcmctree_mock"), tmp_path, name, burnin=10 if big else 40, nsample=16 if big else 60)
 
 
 @pytest.mark.gpu
