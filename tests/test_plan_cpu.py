@@ -162,3 +162,44 @@ def test_program_ps_on_synthetic_trees(shape, ns):
     r = oracle.lnl(p)
     v, lnf = run_program_ps(prog, p, _pmat_fn(p))
     assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
+
+
+def _random_multifurcating_newick(ns, rng, pmulti=0.35):
+    """Random rooted tree as a Newick string in which a join takes 2, 3 or 4 lineages (multifurcations at any depth)."""
+    items = ["%d:%.5f" % (i + 1, rng.uniform(0.02, 0.3)) for i in range(ns)]
+    while len(items) > 4:
+        k = 2 + (rng.random() < pmulti) + (rng.random() < pmulti / 2)
+        idx = sorted(rng.choice(len(items), min(k, len(items) - 1), replace=False))
+        grp = [items[i] for i in idx]
+        items = [x for i, x in enumerate(items) if i not in idx] + ["(%s):%.5f" % (",".join(grp), rng.uniform(0.02, 0.3))]
+    return "(" + ",".join(items) + ");"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_programs_on_random_multifurcating_trees(seed):
+    """Both codon planners (the warp-independent kernel's op stream with folded multifurcations, and the P-stationary kernel's
+    gather ops + step table) on random trees with multifurcations at any depth and random scaling nodes: interpreted in numpy,
+    they must give the oracle's value, and the interpreters' liveness assertions (no slot overwritten while live, G slots rewritten
+    only after they were read, k fields = writes per chunk) must hold."""
+    from paml_b200.tree import parse_newick
+    from simprog import run_program_ps
+    rng = np.random.default_rng(1000 + seed)
+    ns = int(rng.integers(4, 40))
+    p = simulate.nuc_gtr_gamma_problem(ns=ns, npatt=120, seed=50 + seed, K=2)
+    t = parse_newick(_random_multifurcating_newick(ns, rng))
+    p.father, p.nson, p.sons, p.root, p.nnode, p.maxsons = t.father, t.nson, t.sons, t.root, t.nnode, t.maxsons
+    p.branch_t = np.array([1.0, 0.5])[:, None] * t.branch[None, :]
+    p.branch_set = np.zeros((2, t.nnode), np.int32)
+    flags = np.zeros(t.nnode, np.uint8)
+    internal = [v for v in range(ns, t.nnode) if v != t.root and any(t.nson[c] > 0 for c in t.sons[v, :t.nson[v]])]
+    for v in internal:
+        if rng.random() < 0.3:
+            flags[v] = 1                       # (nodes whose children are all tips stay unflagged: the P-stationary planner refuses those)
+    p.scale_flags, p.nscale = flags, int(flags.sum())
+    r = oracle.lnl(p)
+    prog, nslots = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags)
+    v, _ = run_program(prog, nslots, p, _pmat_fn(p))
+    assert abs(v - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
+    progps, _ = likelihood.plan_tree(p.nnode, p.ns, p.root, p.nson, p.sons, p.scale_flags, ps=True)
+    v2, _ = run_program_ps(progps, p, _pmat_fn(p))
+    assert abs(v2 - r["neg_lnL"]) <= 1e-10 * abs(r["neg_lnL"])
