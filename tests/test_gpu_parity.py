@@ -305,3 +305,13 @@ def test_many_contexts_take_turns():
     finally:
         for t in ctxs:
             t.close()
+
+
+@pytest.mark.parametrize("ns", [3, 4, 5, 6])
+def test_tiny_trees_default_dispatch(tl, ns):
+    """Three to six taxa (a star tree at three: the root's children are all tips -- the P-stationary kernel's three-tip gather op and
+    its step without a contraction), through the default dispatch, which picks the P-stationary kernel for alignments this small."""
+    p = simulate.codon_m0_problem(ns=ns, npatt=150, seed=60 + ns)
+    _check_against_oracle(tl, p)
+    assert "prune_ps_kernel" in tl.last_kernel()
+    _check_against_oracle(tl, simulate.add_ambiguity(simulate.codon_m0_problem(ns=ns, npatt=90, seed=70 + ns), 0.1))
