@@ -1,5 +1,6 @@
+"""One cold solve of the device eigen-solver (61 x 61) for ncu: PB200_EIGEN_WARM=0.  usage: ncu ... python tools/eig_prof.py"""
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from paml_b200.likelihood import TreeLikelihood
 os.environ["PB200_EIGEN_WARM"] = "0"
